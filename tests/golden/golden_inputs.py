@@ -1,0 +1,142 @@
+"""Deterministic inputs / weights shared by ``make_golden.py`` (reference side, build
+container) and the tests (oracle + CUDA side, anywhere).  ``numpy.random.RandomState`` is a
+frozen legacy stream, so the same seed gives the same bits on every platform; nothing here
+reads /root/reference.
+"""
+import numpy as np
+import torch
+
+POSE_FILE_0 = "assets/pose_files/2f25826f0d0ef09a.txt"
+POSE_FILE_1 = "assets/pose_files/2c80f9eb0d3b2bb4.txt"
+THETA_SEED = 1234  # torch.manual_seed before each reference call that draws the first-frame slope
+
+
+def _randn(seed, *shape, scale=1.0):
+    return torch.from_numpy((np.random.RandomState(seed).standard_normal(shape) * scale).astype(np.float32))
+
+
+def hidden_tokens(R, N, C, seed):
+    return _randn(seed, R, N, C)
+
+
+def hidden_video(B, C, Fr, h, w, seed):
+    return _randn(seed, B, C, Fr, h, w)
+
+
+def _linear(seed, out_f, in_f, gain=1.0):
+    return _randn(seed, out_f, in_f, scale=gain / np.sqrt(in_f))
+
+
+def attn_state_dict(C, seed, prefix=""):
+    """to_q/to_k/to_v (no bias), to_out.0 (+bias) -- names as in SURVEY.md section 4.3."""
+    return {
+        prefix + "to_q.weight": _linear(seed + 11, C, C, 1.5),
+        prefix + "to_k.weight": _linear(seed + 12, C, C, 1.5),
+        prefix + "to_v.weight": _linear(seed + 13, C, C, 1.0),
+        prefix + "to_out.0.weight": _linear(seed + 14, C, C, 1.0),
+        prefix + "to_out.0.bias": _randn(seed + 15, C, scale=0.1),
+    }
+
+
+def _block_state_dict(C, seed, prefix):
+    sd = {}
+    for i in range(2):
+        sd.update(attn_state_dict(C, seed + 100 * (i + 1), f"{prefix}attention_blocks.{i}."))
+        sd[f"{prefix}norms.{i}.weight"] = 1.0 + _randn(seed + 31 + i, C, scale=0.1)
+        sd[f"{prefix}norms.{i}.bias"] = _randn(seed + 41 + i, C, scale=0.1)
+    sd[prefix + "ff.net.0.proj.weight"] = _linear(seed + 51, 8 * C, C)
+    sd[prefix + "ff.net.0.proj.bias"] = _randn(seed + 52, 8 * C, scale=0.1)
+    sd[prefix + "ff.net.2.weight"] = _linear(seed + 53, C, 4 * C)
+    sd[prefix + "ff.net.2.bias"] = _randn(seed + 54, C, scale=0.1)
+    sd[prefix + "ff_norm.weight"] = 1.0 + _randn(seed + 55, C, scale=0.1)
+    sd[prefix + "ff_norm.bias"] = _randn(seed + 56, C, scale=0.1)
+    return sd
+
+
+def _transformer_state_dict(C, seed, prefix):
+    sd = {
+        prefix + "norm.weight": 1.0 + _randn(seed + 1, C, scale=0.1),
+        prefix + "norm.bias": _randn(seed + 2, C, scale=0.1),
+        prefix + "proj_in.weight": _linear(seed + 3, C, C),
+        prefix + "proj_in.bias": _randn(seed + 4, C, scale=0.1),
+        # proj_out is zero-initialised by the reference (epi_module.py:81-82) which would make
+        # the module an identity: the fixtures use a NON-zero proj_out (SURVEY.md hard part 5).
+        prefix + "proj_out.weight": _linear(seed + 5, C, C, 0.5),
+        prefix + "proj_out.bias": _randn(seed + 6, C, scale=0.1),
+    }
+    sd.update(_block_state_dict(C, seed + 1000, prefix + "transformer_blocks.0."))
+    return sd
+
+
+def module_state_dict(C, seed):
+    return _transformer_state_dict(C, seed, "epi_transformer.")
+
+
+def temporal_state_dict(C, seed):
+    sd = _transformer_state_dict(C, seed, "temporal_transformer.")
+    p = "temporal_transformer.transformer_blocks.0.attention_blocks.0.processor.qkv_merge."
+    # zero-initialised in the reference (attention_processor.py:249-251); non-zero here
+    sd[p + "weight"] = _linear(seed + 7, C, C, 0.5)
+    sd[p + "bias"] = _randn(seed + 8, C, scale=0.1)
+    return sd
+
+
+def view_pair_index(V, n_frames=16):
+    """kv_index pairing view v with V-1-v (a perfect matching like
+    pipeline_animation_epi_advanced.py:625-633 draws), as numpy int64 like the pipeline's."""
+    idx = np.concatenate([np.arange(n_frames) + (V - 1 - v) * n_frames for v in range(V)])
+    return idx.astype(np.int64)
+
+
+def tile_F(Fm, R):
+    """[32,3,3] golden matrices -> [R,3,3]: alternate the matrices and their frame-flipped copy."""
+    reps = [Fm if i % 2 == 0 else Fm.flip(0) for i in range((R + 31) // 32)]
+    return torch.cat(reps, dim=0)[:R].contiguous()
+
+
+ATTN_CASES = [
+    dict(name="swap", C=320, feat=4, R=32, seed=100),
+    dict(name="swap_theta", C=320, feat=4, R=32, seed=200, rand_slope=True, rows=2),
+    dict(name="swap_f8", C=320, feat=8, R=32, seed=300, queries=4),
+    dict(name="kvidx", C=320, feat=4, R=64, seed=400, kv="pair", rows=2),
+    dict(name="multi", C=320, feat=4, R=32, seed=500, kv="multi", rows=2),
+    dict(name="fixff", C=320, feat=4, R=64, seed=600, fix_firstframe=True, rows=2),
+    dict(name="chunk", C=64, feat=4, R=208, seed=700),
+    dict(name="c640", C=640, feat=4, R=32, seed=800, rows=2),
+]
+
+
+def stored(case, out):
+    """The fixtures keep every ``rows``-th row and every ``queries``-th query of an output."""
+    return out[::case.get("rows", 1), ::case.get("queries", 1)]
+
+
+def attn_F_input(case, Fm):
+    R = case["R"]
+    if case.get("kv") == "pair":
+        return [tile_F(Fm, R), view_pair_index(R // 16)]
+    if case.get("kv") == "multi":
+        half = np.concatenate([np.arange(R // 2, R), np.arange(0, R // 2)])
+        return [tile_F(Fm, 2 * R), np.concatenate([half, np.arange(R)]).astype(np.int64)]
+    return tile_F(Fm, R)
+
+
+MODULE_CASES = [
+    dict(name="mod", C=320, feat=4, B=2, seed=1100),
+    dict(name="mod_theta", C=320, feat=4, B=2, seed=1200, rand_slope=True),
+    dict(name="mod_kvidx", C=320, feat=4, B=4, seed=1300, kv="pair"),
+]
+
+
+def module_F_input(case, Fm):
+    B = case["B"]
+    F4 = tile_F(Fm, B * 16).reshape(B, 16, 3, 3)
+    if case.get("kv") == "pair":
+        return [F4, view_pair_index(B)]
+    return F4
+
+
+TEMPORAL_CASES = [
+    dict(name="tmp_pose", C=320, feat=4, B=2, seed=2100, pose=True),
+    dict(name="tmp_nopose", C=320, feat=4, B=2, seed=2200, pose=False),
+]

@@ -1,0 +1,182 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference in the build container.
+
+    python tests/golden/make_golden.py            # needs /root/reference (absent on the GPU box)
+
+The reference's hot-path files are imported verbatim from /root/reference behind
+``oracle/diffusers_shim.py`` (diffusers 0.24.0 is pinned by the reference but is not
+installable here).  Inputs and weights are NOT stored: they are regenerated from
+``golden_inputs.py`` (numpy Generator streams, platform-stable), so the fixtures hold only
+reference OUTPUTS plus a few input checksums.  The committed fixtures pin the oracle
+(tests/test_oracle_golden.py, CPU) and the CUDA path (tests/test_gpu_*.py).
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("CVD_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+sys.path.insert(0, HERE)
+
+from oracle import diffusers_shim  # noqa: E402
+
+diffusers_shim.install()
+
+import golden_inputs as gi  # noqa: E402
+from animatediff.data.dataset_validation import ValRealEstate10KPoseFolded  # noqa: E402
+from animatediff.models.attention_processor import (AttnProcessor, EpiAttnProcessor,  # noqa: E402
+                                                    PoseAdaptorAttnProcessor)
+from animatediff.models.epi_module import EpiEncoding, EpiModule, EpiSelfAttention  # noqa: E402
+from animatediff.models.motion_module import VanillaTemporalModule  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def save(name, **arrays):
+    out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(f"wrote {name}.npz  ({sum(a.nbytes for a in out.values()) / 1e6:.2f} MB raw)")
+
+
+def geometry():
+    ds = ValRealEstate10KPoseFolded(sample_n_frames=16, relative_pose=True, sample_size=256,
+                                    validation_prompts=["x"],
+                                    pose_file_0=os.path.join(REF, gi.POSE_FILE_0),
+                                    pose_file_1=os.path.join(REF, gi.POSE_FILE_1))
+    s = ds[0]
+    pl = s["plucker_embedding"].double()
+    save("geometry", F_mats=s["F_mats"], K_mats=s["ret_K_mats"], c2w=s["ret_c2w"],
+         plucker_sum=pl.sum().item(), plucker_abs_sum=pl.abs().sum().item())
+    return s["F_mats"]
+
+
+def bias(Fm):
+    out = {}
+    for feat in (32, 16, 8, 4):
+        N = feat * feat
+        for tag, rand in (("h", False), ("t", True)):
+            enc = EpiEncoding(320, max_feat_size=64, F_mat_size=256, rand_slope_on_first_frame=rand)
+            torch.manual_seed(gi.THETA_SEED)
+            b = enc.get_attn_map(torch.zeros(32, N, 1), Fm)
+            torch.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0, out=b)
+            k = f"f{feat}{tag}_"
+            out[k + "sum"] = b.double().sum().item()
+            out[k + "min"] = b.min().item()
+            out[k + "zeros"] = int((b == 0).sum())
+            out[k + "rowsum"] = b.double().sum(dim=(1, 2))
+            out[k + "q0"] = b[:, 0, :].clone()               # [32,N] query 0 of every row
+            out[k + "qmid"] = b[:, N // 2 + 3, :].clone()
+            out[k + "diag"] = torch.diagonal(b, dim1=1, dim2=2).clone()
+            if feat <= 8:
+                out[k + "full"] = b.clone()
+    torch.manual_seed(gi.THETA_SEED)
+    out["theta"] = (torch.rand([1]) * math.pi).item()
+    # degenerate inputs: zero F on a non-first-frame row, non-finite F
+    Fbad = Fm.clone()
+    Fbad[3] = 0.0
+    Fbad[5, 0, 0] = float("nan")
+    Fbad[7, 1, 2] = float("inf")
+    enc = EpiEncoding(320, max_feat_size=64, F_mat_size=256, rand_slope_on_first_frame=False)
+    b = enc.get_attn_map(torch.zeros(32, 64, 1), Fbad)
+    torch.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0, out=b)
+    out["bad_full"] = b
+    # a different F_mat_size (image height 512 -> S=512) at feat 8
+    enc = EpiEncoding(320, max_feat_size=64, F_mat_size=512, rand_slope_on_first_frame=False)
+    out["s512_f8_full"] = enc.get_attn_map(torch.zeros(32, 64, 1), Fm)
+    save("bias", **out)
+
+
+def make_attn(C, **kw):
+    attn = EpiSelfAttention(attention_mode="Epi_Self", cross_attention_dim=None, query_dim=C, heads=8,
+                            dim_head=C // 8, dropout=0.0, bias=False, upcast_attention=False,
+                            epi_position_encoding=True, epi_position_encoding_feat_max_size=64,
+                            epi_position_encoding_F_mat_size=256, **kw)
+    attn.set_processor(EpiAttnProcessor(hidden_size=C))
+    return attn
+
+
+def attention(Fm):
+    out = {}
+    for case in gi.ATTN_CASES:
+        name, C, feat, R = case["name"], case["C"], case["feat"], case["R"]
+        attn = make_attn(C, epi_rand_slope_ff=case.get("rand_slope", False),
+                         epi_fix_firstframe=case.get("fix_firstframe", False))
+        sd = gi.attn_state_dict(C, case["seed"])
+        missing, unexpected = attn.load_state_dict(sd, strict=False)
+        assert not unexpected and all("pos_encoder" in m for m in missing), (missing, unexpected)
+        x = gi.hidden_tokens(R, feat * feat, C, case["seed"] + 1)
+        F_in = gi.attn_F_input(case, Fm)
+        torch.manual_seed(gi.THETA_SEED)
+        y, aux = attn(x, F_mats=F_in, pose_feature=None, scale=None)
+        out[name + "_out"] = gi.stored(case, y).clone()
+        out[name + "_xsum"] = x.double().sum().item()
+        if aux is not None:
+            out[name + "_qsum"] = aux["query"].double().abs().sum().item()
+            out[name + "_ksum"] = aux["key"].double().abs().sum().item()
+            out[name + "_key0"] = aux["key"][0, ::case.get("queries", 1)].clone()
+        else:
+            out[name + "_aux_none"] = 1
+    save("attention", **out)
+
+
+def module(Fm):
+    out = {}
+    for case in gi.MODULE_CASES:
+        name, C, feat, B = case["name"], case["C"], case["feat"], case["B"]
+        m = EpiModule(C, num_attention_heads=8, num_transformer_block=1,
+                      attention_block_types=["Epi_Self", "Epi_Self"], epi_position_encoding=True,
+                      epi_position_encoding_feat_max_size=64, epi_position_encoding_F_mat_size=256,
+                      epi_rand_slope_ff=case.get("rand_slope", False), zero_initialize=True)
+        for mod in m.modules():
+            if isinstance(mod, EpiSelfAttention):
+                mod.set_processor(EpiAttnProcessor(hidden_size=C))
+        sd = gi.module_state_dict(C, case["seed"])
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("pos_encoder" in k for k in missing), (missing, unexpected)
+        x = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 1)
+        F_in = gi.module_F_input(case, Fm)
+        torch.manual_seed(gi.THETA_SEED)
+        y, aux = m(x, F_mats=F_in)
+        out[name + "_out"] = y
+        out[name + "_naux"] = len(aux)
+        if case.get("rand_slope", False):
+            torch.manual_seed(gi.THETA_SEED)
+            out[name + "_thetas"] = np.array([(torch.rand([1]) * math.pi).item() for _ in range(2)])
+    save("module", **out)
+
+
+def temporal():
+    out = {}
+    for case in gi.TEMPORAL_CASES:
+        name, C, feat, B = case["name"], case["C"], case["feat"], case["B"]
+        m = VanillaTemporalModule(C, num_attention_heads=8, num_transformer_block=1,
+                                  attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                  temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                  zero_initialize=False)
+        blk = m.temporal_transformer.transformer_blocks[0]
+        p0 = PoseAdaptorAttnProcessor(hidden_size=C, pose_feature_dim=C, query_condition=True,
+                                      key_value_condition=True, scale=1.0)
+        blk.attention_blocks[0].set_processor(p0)
+        blk.attention_blocks[1].set_processor(AttnProcessor(attn_type="temporal"))
+        sd = gi.temporal_state_dict(C, case["seed"])
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("pos_encoder" in k for k in missing), (missing, unexpected)
+        x = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 1)
+        pose = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 2) if case["pose"] else None
+        y = m(x, cross_attention_kwargs={"pose_feature": pose})
+        out[name + "_out"] = y
+    save("temporal", **out)
+
+
+if __name__ == "__main__":
+    Fm = geometry()
+    bias(Fm)
+    attention(Fm)
+    module(Fm)
+    temporal()
