@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the CVD epipolar cross-view attention hot path (BASELINE.json metric:
+epi-attn TFLOP/s and % of bf16 tensor peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE config 2, two-video inference on one B200): R = 64 rows (2 views x 2 CFG
+branches x 16 frames); one STEP = the 40 epi-attention calls of one UNet forward, 10 each at
+(N, C) = (1024, 320), (256, 640), (64, 1280), (16, 1280), 8 heads, real pose-pair geometry,
+random-init weights, synthetic unit-variance activations.  Algorithmic work per step =
+sum 4*R*N*N*C = 15.32 GFLOP * R (softmax, bias and MMA padding excluded).
+
+  value : TFLOP/s of the step with q / k / v^T / F_mats resident in HBM (row-table prepass + the
+          fused tcgen05 kernel per call; distinct buffers per call, 1.9 GB per step >> L2).
+  e2e   : the same metric through the drop-in layer API (EpiSelfAttention.forward) with HOST
+          buffers: per call, H2D of the fp32 hidden states from pinned memory, projections, bias
+          prepass, fused attention, output projection, D2H of the result.
+  --impl reference : the reference's CPU path (oracle port of EpiSelfAttention.forward, fp32,
+          all host threads) on a bounded sample of the same step (one call per shape).
+At N > 1 the views shard across ranks (weak scaling: 64 rows per GPU, 2N views); every call
+all-gathers K and V^T over NCCL and the kernel indexes the gathered buffer.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SHAPES = [(32, 320), (16, 640), (8, 1280), (4, 1280)]   # (feat, C) of epi_module_resolutions [1,2,4,8] at 256x256
+CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 attention blocks per resolution
+HEADS = 8
+R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
+F_MAT_SIZE = 256
+
+
+def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
+    return sum(calls * 4.0 * R * (f * f) ** 2 * C for f, C in shapes)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["bf16_tflops"]), float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst)"
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def golden_F():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))
+    return torch.from_numpy(g["F_mats"])          # [32,3,3]: rows 0-15 view A->B, 16-31 view B->A
+
+
+def cfg_F_mats(n_views_pairs=1):
+    """[R,3,3] in the sampler's CFG layout [U-src, C-src, U-tgt, C-tgt] (pipeline_animation_epi.py:565-571)."""
+    Fm = golden_F()
+    src, tgt = Fm[:16], Fm[16:]
+    return torch.cat([src, src, tgt, tgt], dim=0).repeat(n_views_pairs, 1, 1).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: oracle port of the reference's CPU path
+# ------------------------------------------------------------------------------------------
+def cpu_reference_step(R, reps, warm):
+    """Times the oracle's EpiSelfAttention.forward (fp32, all host threads) on a bounded sample of
+    the step: ONE call per shape.  Returns (seconds per sample step, flops per sample step, cores)."""
+    import golden_inputs as gi
+    from oracle import epi_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Fm = cfg_F_mats(R // 64)
+    cases = []
+    for feat, C in SHAPES:
+        sd = gi.attn_state_dict(C, 10 + feat)
+        x = torch.randn(R, feat * feat, C, generator=torch.Generator().manual_seed(feat))
+        cases.append((x, sd, Fm))
+    flops = step_flops(R, calls=1)
+
+    def one():
+        with torch.no_grad():
+            for x, sd, F_ in cases:
+                O.epi_self_attention(x, sd, "", HEADS, F_, F_MAT_SIZE, theta=0.5)
+
+    for _ in range(warm):
+        one()
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    return times, flops, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R = R_PER_GPU * args.gpus
+    warm = min(args.warmup, 1)
+    times, flops, cores = cpu_reference_step(R, args.steps, warm)
+    total = sum(times)
+    val = flops * len(times) / total / 1e12
+    sample = f"1 of the {CALLS_PER_SHAPE} calls per shape per step (4 calls, {flops / 1e9:.1f} GFLOP), fp32, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "epi_attn_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "CVD two-video inference (BASELINE config 2): 40 epi-attention calls of one UNet forward, "
+                        "R=64 rows per GPU (2 views x 2 cfg x 16 frames), (N,C) = (1024,320),(256,640),(64,1280),(16,1280) x10, 8 heads",
+            "rows_per_gpu": R_PER_GPU, "views_total": 2 * n_gpus, "flops_per_step": step_flops(R_PER_GPU * n_gpus),
+            "parallelism": "1 GPU" if n_gpus == 1 else f"views sharded over {n_gpus} GPUs, K/V^T all-gather per call (NCCL)",
+            "l2_policy": "inputs larger than L2: distinct q/k/v^T buffers per call (1.9 GB per step)"}
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import cvd_b200
+    import golden_inputs as gi
+    from cvd_b200 import _lib, ops, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    shard = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        shard = sharding.ViewShard()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    _lib.load()
+    R = R_PER_GPU
+    R_glob = R * world
+    peak_tf, peak_bw, peak_src = load_peaks()
+
+    # geometry of this rank's rows + partner rows (global numbering when sharded)
+    F_rows = cfg_F_mats(1).to(dev)                                 # same pose pair on every rank
+    if shard is None:
+        partner = torch.cat([torch.arange(R // 2, R), torch.arange(0, R // 2)]).to(torch.int32).to(dev)
+    else:
+        # view v pairs with the view half the ring away (always on another rank when world > 1)
+        glob = (np.arange(R_glob) + R_glob // 2) % R_glob
+        partner = torch.from_numpy(shard.local_kv_index(glob, R_glob).astype(np.int32)).to(dev)
+
+    # ---------------- value: kernels only, inputs resident ----------------
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    bufs = []
+    for feat, C in SHAPES:
+        N, d = feat * feat, C // HEADS
+        per_call = []
+        for _ in range(CALLS_PER_SHAPE):
+            q = torch.randn(R, N, C, device=dev, generator=gen).to(torch.bfloat16)
+            k = torch.randn(R, N, C, device=dev, generator=gen).to(torch.bfloat16)
+            vt = torch.zeros(R, HEADS, ops.dv_rows(d), N, device=dev, dtype=torch.bfloat16)
+            vt[:, :, :d] = torch.randn(R, HEADS, d, N, device=dev, generator=gen).to(torch.bfloat16)
+            vt[:, :, d] = 1.0
+            per_call.append((q, k, vt))
+        bufs.append(per_call)
+    theta = torch.tensor([0.5], device=dev)
+    big_events = []
+
+    def value_step(record):
+        for (feat, C), per_call in zip(SHAPES, bufs):
+            for q, k, vt in per_call:
+                rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
+                ks, vs = (k, vt) if shard is None else (shard.gather_rows(k), shard.gather_rows(vt))
+                if record and feat == SHAPES[0][0]:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    ops.epi_attn_fwd(q, ks, vs, rowp, partner, HEADS, F_MAT_SIZE)
+                    e1.record()
+                    big_events.append((e0, e1))
+                else:
+                    ops.epi_attn_fwd(q, ks, vs, rowp, partner, HEADS, F_MAT_SIZE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        value_step(False)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = ops.LAUNCHES
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        value_step(True)
+    t1.record()
+    barrier()
+    launches = ops.LAUNCHES - launches0
+    ms_value = t0.elapsed_time(t1) / args.steps
+    clk = clocks.stop()
+    big_ms = float(np.mean([a.elapsed_time(b) for a, b in big_events]))
+
+    # ---------------- e2e: layer API with host buffers ----------------
+    layers, hosts = [], []
+    for feat, C in SHAPES:
+        attn = cvd_b200.EpiSelfAttention(attention_mode="Epi_Self", cross_attention_dim=None, query_dim=C, heads=HEADS,
+                                         dim_head=C // HEADS, epi_position_encoding=True,
+                                         epi_position_encoding_feat_max_size=64,
+                                         epi_position_encoding_F_mat_size=F_MAT_SIZE, epi_rand_slope_ff=True)
+        attn.load_state_dict(gi.attn_state_dict(C, 10 + feat), strict=False)
+        attn = attn.to(dev).eval()
+        attn.processor.shard = shard
+        layers.append(attn)
+        x_host = torch.randn(R, feat * feat, C, generator=torch.Generator().manual_seed(feat)).pin_memory()
+        y_host = torch.empty_like(x_host).pin_memory()
+        hosts.append((x_host, y_host))
+    kv_index = None if shard is None else partner.cpu().numpy().astype(np.int64)
+    h2d = sum(CALLS_PER_SHAPE * x.numel() * 4 for x, _ in hosts)
+    d2h = h2d
+
+    def e2e_step():
+        with torch.no_grad():
+            for attn, (x_host, y_host) in zip(layers, hosts):
+                for _ in range(CALLS_PER_SHAPE):
+                    x = x_host.to(dev, non_blocking=True)
+                    y, _aux = attn(x, F_mats=F_rows if kv_index is None else [F_rows, kv_index])
+                    y_host.copy_(y, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e_steps = max(3, min(args.steps, 10))
+    t0.record()
+    for _ in range(e_steps):
+        e2e_step()
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1) / e_steps
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_value, ms_e2e, big_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_value, ms_e2e, big_ms = (float(v) for v in tt.tolist())
+    flops = step_flops(R_glob)
+    big_flops = 4.0 * R * 1024 * 1024 * 320
+    achieved = big_flops / (big_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        cb_times, cb_flops, cores = cpu_reference_step(R, reps=2, warm=1)
+        cb_val = cb_flops / min(cb_times) / 1e12
+        line = {
+            "metric": "epi_attn_tflops", "value": flops / (ms_value * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "cvd_b200.EpiSelfAttention.forward (fp32 host tensors, pinned)"},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "epi_attn_fwd_kernel<40,32> (R=64, N=M=1024, C=320)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "peak_source": peak_src, "ms_per_launch": big_ms,
+                         "algorithmic_flops_per_launch": big_flops},
+            "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                             "sample": f"oracle EpiSelfAttention.forward, 1 call per shape ({cb_flops / 1e9:.1f} GFLOP), best of 2"},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

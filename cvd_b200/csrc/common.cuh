@@ -1,0 +1,79 @@
+// Shared helpers of the cvd_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/cvd_b200.h"
+
+namespace cvd {
+
+// thread-local message behind cvd_last_error()
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+
+#define CVD_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return ::cvd::fail(CVD_E_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define CVD_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ::cvd::fail(CVD_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
+  } while (0)
+
+#define CVD_LAUNCH_CHECK(name)                                                           \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess)                                                              \
+      return ::cvd::fail(CVD_E_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Pixel-centre coordinate of latent index i in F_mat_size space (epi_module.py:298):
+//   x = (S/feat) * i + (S/feat - 1) / 2
+__host__ __device__ __forceinline__ float pixel_centre(int i, float step) {
+  return step * (float)i + (step - 1.0f) * 0.5f;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_as_float(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+  return __bfloat162float(p[i]);
+}
+template <>
+__device__ __forceinline__ float load_as_float<__half>(const __half* p, size_t i) { return __half2float(p[i]); }
+
+template <typename T>
+__device__ __forceinline__ void store_from_float(T* p, size_t i, float v);
+template <>
+__device__ __forceinline__ void store_from_float<float>(float* p, size_t i, float v) { p[i] = v; }
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, size_t i, float v) {
+  p[i] = __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ void store_from_float<__half>(__half* p, size_t i, float v) { p[i] = __float2half_rn(v); }
+
+}  // namespace cvd

@@ -1,0 +1,375 @@
+// HBM-bound glue around the epi / temporal attention: GroupNorm + token layout, LayerNorm,
+// GEGLU, residual updates and the inverse layout.  All kernels are coalesced on both the
+// read and the write side (layout changes go through a padded shared-memory tile), use
+// 8/16-byte vector accesses where the shape allows and warp-shuffle reductions.
+#include "common.cuh"
+
+namespace cvd {
+
+// token index of (b, f, p) in the two layouts the reference uses
+__device__ __forceinline__ size_t token_of(int b, int f, int p, int F, int HW, int layout) {
+  return layout == CVD_LAYOUT_BF_HW ? ((size_t)b * F + f) * HW + p : ((size_t)b * HW + p) * F + f;
+}
+
+// ---------------------------------------------------------------------------------------
+// GroupNorm statistics: one CTA per (b, f, group).  resnet.py:30-40 applies nn.GroupNorm
+// per frame, so a group is cpg channels x HW pixels of ONE frame (channel stride F*HW).
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats,
+                                                              int C, int F, int HW, int groups, float eps) {
+  const int g = blockIdx.x % groups;
+  const int f = (blockIdx.x / groups) % F;
+  const int b = blockIdx.x / (groups * F);
+  const int cpg = C / groups;
+  const int n = cpg * HW;
+  const T* base = x + (((size_t)b * C + (size_t)g * cpg) * F + f) * HW;
+  const size_t cstride = (size_t)F * HW;
+  __shared__ float red[8];
+  __shared__ float bc;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += load_as_float(base, (size_t)(i / HW) * cstride + (i % HW));
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    bc = t / (float)n;
+  }
+  __syncthreads();
+  const float mean = bc;
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = load_as_float(base, (size_t)(i / HW) * cstride + (i % HW)) - mean;
+    v = fmaf(d, d, v);
+  }
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    stats[2 * (size_t)blockIdx.x] = mean;
+    stats[2 * (size_t)blockIdx.x + 1] = rsqrtf(t / (float)n + eps);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// video [B,C,F,HW] -> bf16 tokens [T, C] through a 64-channel x 32-pixel tile.
+//   MODE 0: y = groupnorm(x)                (epi_module.py:163-165, motion_module.py:377-378)
+//   MODE 1: y = tok_in + x                  (pose feature add, attention_processor.py:325)
+// ---------------------------------------------------------------------------------------
+constexpr int kTileC = 64, kTileP = 32;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+video_to_tokens_kernel(const T* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const __nv_bfloat16* __restrict__ tok_in,
+                       __nv_bfloat16* __restrict__ y, int C, int F, int HW, int groups, int layout) {
+  __shared__ float tile[kTileC][kTileP + 1];
+  const int p0 = blockIdx.x * kTileP, c0 = blockIdx.y * kTileC;
+  const int f = blockIdx.z % F, b = blockIdx.z / F;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int cpg = C / groups;
+#pragma unroll
+  for (int i = 0; i < kTileC / 8; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    float v = 0.f;
+    if (c < C && p < HW) {
+      v = load_as_float(x, (((size_t)b * C + c) * F + f) * HW + p);
+      if (MODE == 0) {
+        const float* st = stats + 2 * ((size_t)(b * F + f) * groups + c / cpg);
+        v = (v - st[0]) * st[1] * gamma[c] + beta[c];
+      }
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+  // write: 32 lanes cover 64 channels (2 each) of one token -> 128-byte rows
+#pragma unroll
+  for (int i = 0; i < kTileP / 8; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + 2 * tx;
+    if (p < HW && c < C) {
+      const size_t o = token_of(b, f, p, F, HW, layout) * C + c;
+      float v0 = tile[2 * tx][ty + 8 * i], v1 = tile[2 * tx + 1][ty + 8 * i];
+      if (MODE == 1) {
+        const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(tok_in + o);
+        v0 += __bfloat162float(t.x);
+        v1 += __bfloat162float(t.y);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(y + o) = __floats2bfloat162_rn(v0, v1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tokens bf16 [T, C] (+bias) -> video layout + residual   (epi_module.py:185-187)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+tokens_to_video_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ bias,
+                       const T* __restrict__ residual, T* __restrict__ out, int C, int F, int HW, int layout) {
+  __shared__ float tile[kTileP][kTileC + 1];
+  const int p0 = blockIdx.x * kTileP, c0 = blockIdx.y * kTileC;
+  const int f = blockIdx.z % F, b = blockIdx.z / F;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < kTileP / 8; ++i) {
+    const int p = p0 + ty + 8 * i, c = c0 + 2 * tx;
+    float v0 = 0.f, v1 = 0.f;
+    if (p < HW && c < C) {
+      const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(tok + token_of(b, f, p, F, HW, layout) * C + c);
+      v0 = __bfloat162float(t.x) + (bias ? bias[c] : 0.f);
+      v1 = __bfloat162float(t.y) + (bias ? bias[c + 1] : 0.f);
+    }
+    tile[ty + 8 * i][2 * tx] = v0;
+    tile[ty + 8 * i][2 * tx + 1] = v1;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kTileC / 8; ++i) {
+    const int c = c0 + ty + 8 * i, p = p0 + tx;
+    if (c < C && p < HW) {
+      const size_t o = (((size_t)b * C + c) * F + f) * HW + p;
+      store_from_float(out, o, load_as_float(residual, o) + tile[tx][ty + 8 * i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm: one warp per token, the row lives in registers (C <= 1280), two-pass variance.
+// ---------------------------------------------------------------------------------------
+template <int PAIRS>   // float2 pairs per lane = C / 64
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const float* __restrict__ pe, __nv_bfloat16* __restrict__ y, int tokens, int seq_len, float eps) {
+  constexpr int C = PAIRS * 64;
+  const int lane = threadIdx.x & 31;
+  const size_t t = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= (size_t)tokens) return;
+  const float2* row = reinterpret_cast<const float2*>(x + t * C);
+  float2 v[PAIRS];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    v[j] = row[lane + 32 * j];
+    s += v[j].x + v[j].y;
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    const float dx = v[j].x - mean, dy = v[j].y - mean;
+    q = fmaf(dx, dx, fmaf(dy, dy, q));
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma);
+  const float2* b2 = reinterpret_cast<const float2*>(beta);
+  const float2* p2 = pe ? reinterpret_cast<const float2*>(pe + (t % seq_len) * C) : nullptr;
+  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(y + t * C);
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    const int i = lane + 32 * j;
+    const float2 g = g2[i], b = b2[i];
+    float ox = (v[j].x - mean) * rstd * g.x + b.x, oy = (v[j].y - mean) * rstd * g.y + b.y;
+    if (p2) {
+      const float2 p = p2[i];
+      ox += p.x;
+      oy += p.y;
+    }
+    out[i] = __floats2bfloat162_rn(ox, oy);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GEGLU: out = h * gelu_erf(g), 8 bf16 (16 bytes) per thread.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ hg, uint4* __restrict__ out,
+                                                    size_t tokens, int inner8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tokens * inner8) return;
+  const size_t t = i / inner8, c = i % inner8;
+  const uint4 hv = hg[t * 2 * inner8 + c], gv = hg[t * 2 * inner8 + inner8 + c];
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hv);
+  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+  uint4 ov;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 h = __bfloat1622float2(h2[j]), g = __bfloat1622float2(g2[j]);
+    o2[j] = __floats2bfloat162_rn(h.x * gelu_erf(g.x), h.y * gelu_erf(g.y));
+  }
+  out[i] = ov;
+}
+
+// ---------------------------------------------------------------------------------------
+// x += (y + bias) * scale   (fp32 residual stream), optional bf16 copy; 4 elements per thread.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+residual_add_kernel(float4* __restrict__ x, const uint2* __restrict__ y, const float4* __restrict__ bias, float scale,
+                    uint2* __restrict__ xb, size_t n4, int C4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 xv = x[i];
+  const uint2 yv = y[i];
+  const float2 y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.x));
+  const float2 y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv.y));
+  float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b = bias[i % C4];
+  xv.x += (y0.x + b.x) * scale;
+  xv.y += (y0.y + b.y) * scale;
+  xv.z += (y1.x + b.z) * scale;
+  xv.w += (y1.y + b.w) * scale;
+  x[i] = xv;
+  if (xb) {
+    uint2 o;
+    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(xv.x, xv.y);
+    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(xv.z, xv.w);
+    xb[i] = o;
+  }
+}
+
+// out = a * scale + b  (bf16, 8 per thread)   -- attention_processor.py:325
+__global__ void __launch_bounds__(256) scale_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                        float scale, uint4* __restrict__ out, size_t n8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 av = a[i], bv = b[i];
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+  const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bv);
+  uint4 ov;
+  __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(b2[j]);
+    o2[j] = __floats2bfloat162_rn(fmaf(x.x, scale, y.x), fmaf(x.y, scale, y.y));
+  }
+  out[i] = ov;
+}
+
+template <typename T>
+static int launch_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B,
+                                   int C, int F, int HW, int groups, float eps, int layout, cudaStream_t st) {
+  groupnorm_stats_kernel<T><<<B * F * groups, 256, 0, st>>>((const T*)x, stats, C, F, HW, groups, eps);
+  CVD_LAUNCH_CHECK("groupnorm_stats_kernel");
+  dim3 grid((HW + kTileP - 1) / kTileP, (C + kTileC - 1) / kTileC, B * F);
+  video_to_tokens_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, stats, gamma, beta, nullptr, (__nv_bfloat16*)y, C, F,
+                                                     HW, groups, layout);
+  CVD_LAUNCH_CHECK("video_to_tokens_kernel");
+  return CVD_OK;
+}
+
+}  // namespace cvd
+
+using namespace cvd;
+
+extern "C" int cvd_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                                        float* stats, int B, int C, int F, int HW, int groups, float eps, int layout,
+                                        cvd_stream_t stream) {
+  CVD_REQUIRE(x && gamma && beta && y && stats, "cvd_groupnorm_tokens_fwd: null pointer");
+  CVD_REQUIRE(B > 0 && C > 0 && F > 0 && HW > 0 && groups > 0 && C % groups == 0 && C % 2 == 0,
+              "cvd_groupnorm_tokens_fwd: bad shape B=%d C=%d F=%d HW=%d groups=%d", B, C, F, HW, groups);
+  CVD_REQUIRE((long long)B * F <= 65535, "cvd_groupnorm_tokens_fwd: B*F=%lld exceeds the grid limit", (long long)B * F);
+  CVD_REQUIRE(layout == CVD_LAYOUT_BF_HW || layout == CVD_LAYOUT_BHW_F, "cvd_groupnorm_tokens_fwd: layout %d", layout);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x_dtype) {
+    case CVD_DTYPE_F32: return launch_groupnorm_tokens<float>(x, gamma, beta, y, stats, B, C, F, HW, groups, eps, layout, st);
+    case CVD_DTYPE_BF16: return launch_groupnorm_tokens<__nv_bfloat16>(x, gamma, beta, y, stats, B, C, F, HW, groups, eps, layout, st);
+    case CVD_DTYPE_F16: return launch_groupnorm_tokens<__half>(x, gamma, beta, y, stats, B, C, F, HW, groups, eps, layout, st);
+  }
+  return fail(CVD_E_INVALID, "cvd_groupnorm_tokens_fwd: x_dtype %d not supported", x_dtype);
+}
+
+extern "C" int cvd_add_pose_tokens_fwd(const void* x_tok, const void* pose, int pose_dtype, void* out_tok, int B, int C,
+                                       int F, int HW, cvd_stream_t stream) {
+  CVD_REQUIRE(x_tok && pose && out_tok, "cvd_add_pose_tokens_fwd: null pointer");
+  CVD_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && F > 0 && HW > 0 && (long long)B * F <= 65535,
+              "cvd_add_pose_tokens_fwd: bad shape B=%d C=%d F=%d HW=%d", B, C, F, HW);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((HW + kTileP - 1) / kTileP, (C + kTileC - 1) / kTileC, B * F);
+  const __nv_bfloat16* xin = (const __nv_bfloat16*)x_tok;
+  __nv_bfloat16* o = (__nv_bfloat16*)out_tok;
+  if (pose_dtype == CVD_DTYPE_F32)
+    video_to_tokens_kernel<float, 1><<<grid, 256, 0, st>>>((const float*)pose, nullptr, nullptr, nullptr, xin, o, C, F, HW, 1, CVD_LAYOUT_BHW_F);
+  else if (pose_dtype == CVD_DTYPE_BF16)
+    video_to_tokens_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)pose, nullptr, nullptr, nullptr, xin, o, C, F, HW, 1, CVD_LAYOUT_BHW_F);
+  else if (pose_dtype == CVD_DTYPE_F16)
+    video_to_tokens_kernel<__half, 1><<<grid, 256, 0, st>>>((const __half*)pose, nullptr, nullptr, nullptr, xin, o, C, F, HW, 1, CVD_LAYOUT_BHW_F);
+  else
+    return fail(CVD_E_INVALID, "cvd_add_pose_tokens_fwd: pose_dtype %d not supported", pose_dtype);
+  CVD_LAUNCH_CHECK("video_to_tokens_kernel<add>");
+  return CVD_OK;
+}
+
+extern "C" int cvd_tokens_to_video_fwd(const void* tok, const float* bias, const void* residual, void* out, int io_dtype,
+                                       int B, int C, int F, int HW, int layout, cvd_stream_t stream) {
+  CVD_REQUIRE(tok && residual && out, "cvd_tokens_to_video_fwd: null pointer");
+  CVD_REQUIRE(B > 0 && C > 0 && C % 2 == 0 && F > 0 && HW > 0 && (long long)B * F <= 65535,
+              "cvd_tokens_to_video_fwd: bad shape B=%d C=%d F=%d HW=%d", B, C, F, HW);
+  CVD_REQUIRE(layout == CVD_LAYOUT_BF_HW || layout == CVD_LAYOUT_BHW_F, "cvd_tokens_to_video_fwd: layout %d", layout);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((HW + kTileP - 1) / kTileP, (C + kTileC - 1) / kTileC, B * F);
+  const __nv_bfloat16* t = (const __nv_bfloat16*)tok;
+  if (io_dtype == CVD_DTYPE_F32)
+    tokens_to_video_kernel<float><<<grid, 256, 0, st>>>(t, bias, (const float*)residual, (float*)out, C, F, HW, layout);
+  else if (io_dtype == CVD_DTYPE_BF16)
+    tokens_to_video_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(t, bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, C, F, HW, layout);
+  else if (io_dtype == CVD_DTYPE_F16)
+    tokens_to_video_kernel<__half><<<grid, 256, 0, st>>>(t, bias, (const __half*)residual, (__half*)out, C, F, HW, layout);
+  else
+    return fail(CVD_E_INVALID, "cvd_tokens_to_video_fwd: io_dtype %d not supported", io_dtype);
+  CVD_LAUNCH_CHECK("tokens_to_video_kernel");
+  return CVD_OK;
+}
+
+extern "C" int cvd_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* pe, void* y,
+                                 int tokens, int C, int seq_len, float eps, cvd_stream_t stream) {
+  CVD_REQUIRE(x && gamma && beta && y, "cvd_layernorm_fwd: null pointer");
+  CVD_REQUIRE(tokens > 0, "cvd_layernorm_fwd: tokens=%d", tokens);
+  CVD_REQUIRE(!pe || seq_len > 0, "cvd_layernorm_fwd: seq_len must be positive with a positional table");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((tokens + 7) / 8);
+  __nv_bfloat16* o = (__nv_bfloat16*)y;
+  switch (C) {
+    case 64: layernorm_kernel<1><<<grid, 256, 0, st>>>(x, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 320: layernorm_kernel<5><<<grid, 256, 0, st>>>(x, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 640: layernorm_kernel<10><<<grid, 256, 0, st>>>(x, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 1280: layernorm_kernel<20><<<grid, 256, 0, st>>>(x, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    default: return fail(CVD_E_INVALID, "cvd_layernorm_fwd: C=%d not supported (64, 320, 640, 1280)", C);
+  }
+  CVD_LAUNCH_CHECK("layernorm_kernel");
+  return CVD_OK;
+}
+
+extern "C" int cvd_geglu_fwd(const void* hg, void* out, int tokens, int inner, cvd_stream_t stream) {
+  CVD_REQUIRE(hg && out, "cvd_geglu_fwd: null pointer");
+  CVD_REQUIRE(tokens > 0 && inner > 0 && inner % 8 == 0, "cvd_geglu_fwd: tokens=%d inner=%d (inner must be a multiple of 8)", tokens, inner);
+  const size_t n = (size_t)tokens * (inner / 8);
+  geglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)hg, (uint4*)out, (size_t)tokens, inner / 8);
+  CVD_LAUNCH_CHECK("geglu_kernel");
+  return CVD_OK;
+}
+
+extern "C" int cvd_residual_add_fwd(float* x, const void* y, const float* bias, float scale, void* x_bf16, int tokens,
+                                    int C, cvd_stream_t stream) {
+  CVD_REQUIRE(x && y, "cvd_residual_add_fwd: null pointer");
+  CVD_REQUIRE(tokens > 0 && C > 0 && C % 4 == 0, "cvd_residual_add_fwd: tokens=%d C=%d (C must be a multiple of 4)", tokens, C);
+  const size_t n4 = (size_t)tokens * (C / 4);
+  residual_add_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (float4*)x, (const uint2*)y, (const float4*)bias, scale, (uint2*)x_bf16, n4, C / 4);
+  CVD_LAUNCH_CHECK("residual_add_kernel");
+  return CVD_OK;
+}
+
+extern "C" int cvd_scale_add_fwd(const void* a, const void* b, float scale, void* out, long long n, cvd_stream_t stream) {
+  CVD_REQUIRE(a && b && out, "cvd_scale_add_fwd: null pointer");
+  CVD_REQUIRE(n > 0 && n % 8 == 0, "cvd_scale_add_fwd: n=%lld must be a positive multiple of 8", n);
+  const size_t n8 = (size_t)n / 8;
+  scale_add_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, scale, (uint4*)out, n8);
+  CVD_LAUNCH_CHECK("scale_add_kernel");
+  return CVD_OK;
+}

@@ -1,0 +1,461 @@
+"""Drop-in replacement of the reference's cross-video synchronisation module.
+
+Mirrors ``animatediff/models/epi_module.py`` (EpiModule :38, EpiTransformer3DModel :92,
+EpiTransformerBlock :191, EpiEncoding :271, EpiSelfAttention :350) and ``EpiAttnProcessor``
+(``animatediff/models/attention_processor.py:522-650``): same class names, constructor
+arguments, forward signatures, return values and ``state_dict`` keys, so
+``cvd.ckpt["unet_trainable_dict"]`` loads unchanged and ``unet_blocks.py`` can call it as is.
+
+What differs is the execution: every stage runs in hand-written CUDA for sm_100a behind the
+C ABI of ``include/cvd_b200.h`` (dense projections go through cuBLAS via ``F.linear``).
+The dense epipolar mask is never materialised; the fused tcgen05 kernel rebuilds it from a
+12-float-per-row table.  Forward only (inference); there is no CPU path and no fallback.
+"""
+import math
+from typing import Any, Dict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib, ops
+
+FRAMES_PER_VIDEO = 16   # hard-coded by the reference (epi_module.py:316, attention_processor.py:631)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+def get_epi_module(in_channels, epi_module_kwargs: dict):
+    """epi_module.py:32-36."""
+    return EpiModule(in_channels=in_channels, **epi_module_kwargs)
+
+
+class _WeightCache:
+    """bf16 / fp32 device copies of parameters, refreshed when a parameter is modified in place
+    (load_state_dict, optimizer step) or moved."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, key, src, make):
+        tag = (src.data_ptr(), src._version, src.device, src.dtype)
+        hit = self._c.get(key)
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                hit = (tag, make(src))
+            self._c[key] = hit
+        return hit[1]
+
+    def bf16(self, key, p):
+        return self.get(key, p, lambda t: t.detach().to(torch.bfloat16).contiguous())
+
+    def f32(self, key, p):
+        return self.get(key, p, lambda t: t.detach().float().contiguous())
+
+
+def _require_inference(module, *tensors):
+    """Forward only: refuse to run where autograd would expect a graph."""
+    if torch.is_grad_enabled() and (module.training or any(t is not None and t.requires_grad for t in tensors)):
+        raise NotImplementedError(
+            "cvd_b200 implements the forward (inference) path only; the backward kernels are "
+            "SURVEY.md section 8(f3).  Call under torch.no_grad() (or put the module in eval() mode "
+            "with inputs that do not require grad).")
+
+
+class GEGLU(nn.Module):
+    """Parameter holder with diffusers' names: ``ff.net.0.proj``."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+
+class FeedForward(nn.Module):
+    """GEGLU feed-forward with diffusers 0.24 parameter names (``net.0.proj``, ``net.2``)."""
+
+    def __init__(self, dim, dropout=0.0, activation_fn="geglu"):
+        super().__init__()
+        if activation_fn != "geglu":
+            raise ValueError("only activation_fn='geglu' is on the reference hot path")
+        self.net = nn.ModuleList([GEGLU(dim, 4 * dim), nn.Dropout(dropout), nn.Linear(4 * dim, dim)])
+        self._w = _WeightCache()
+
+    def forward_tokens(self, n_bf16):
+        """bf16 [T..., C] (already LayerNorm-ed) -> bf16 [T..., C] WITHOUT the net.2 bias."""
+        w = self._w
+        hg = F.linear(n_bf16, w.bf16("w1", self.net[0].proj.weight), w.bf16("b1", self.net[0].proj.bias))
+        return F.linear(ops.geglu(hg), w.bf16("w2", self.net[2].weight))
+
+
+class EpiEncoding(nn.Module):
+    """epi_module.py:271-346.  Keeps the reference's persistent ``coords`` buffer (state_dict
+    key ``pos_encoder.coords``); the geometry itself is evaluated on the device."""
+
+    def __init__(self, d_model, dropout=0., max_feat_size=128, F_mat_size=256, rand_slope_on_first_frame=False):
+        super().__init__()
+        self.F_mat_size = F_mat_size
+        self.rand_slope_on_first_frame = rand_slope_on_first_frame
+        coords = torch.arange(max_feat_size)
+        cx, cy = torch.meshgrid(coords, coords, indexing="xy")
+        self.register_buffer("coords", torch.stack([cx, cy, cx * 0 + 1], dim=-1))
+        self.theta_override = None   # tests inject the first-frame slope here (device fp32 [1])
+
+    def row_params(self, x, F_mats, pixel_band=3, decay_alpha=3):
+        """Row table [rows,12] for the fused kernel.  Consumes the global RNG exactly like the
+        reference: one ``torch.rand([1], device=...)`` per call when rand_slope is on
+        (epi_module.py:316,335)."""
+        feat = int(x.shape[1] ** 0.5)
+        if feat * feat != x.shape[1]:
+            raise ValueError(f"EpiEncoding needs a square latent, got {x.shape[1]} tokens (epi_module.py:294)")
+        Fm = F_mats.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        theta, rule = None, _lib.FF_HORIZONTAL
+        if self.rand_slope_on_first_frame:
+            rule = _lib.FF_RANDOM_SLOPE
+            if self.theta_override is not None:
+                theta = self.theta_override.to(device=x.device, dtype=torch.float32).reshape(1).contiguous()
+            else:
+                theta = torch.rand([1], device=x.device) * math.pi
+        return ops.epi_row_params(Fm, feat, self.F_mat_size, theta, rule, pixel_band, decay_alpha, FRAMES_PER_VIDEO)
+
+    def get_attn_map(self, x, F_mats=None, H_mats=None, pixel_band=3, decay_alpha=3):
+        """Dense bias [rows, N, N] -- parity/debug API only; the product path never calls it."""
+        if H_mats is not None or F_mats is None:
+            raise NotImplementedError("only the F_mats branch of get_attn_map is built (epi_module.py:311-316)")
+        feat = int(x.shape[1] ** 0.5)
+        return ops.epi_bias_dense(self.row_params(x, F_mats, pixel_band, decay_alpha), feat, self.F_mat_size)
+
+
+class EpiAttnProcessor(nn.Module):
+    """attention_processor.py:522-650.  Parameter-free; installed with ``attn.set_processor``
+    (``unet.set_all_attn_processor``) exactly like the reference's.  It receives the row table
+    (``epi_rowp``) where the reference's processor receives the dense ``attention_mask``."""
+
+    def __init__(self, hidden_size, scale=1.0):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.scale = scale
+        self._idx = {}
+        self.shard = None   # cvd_b200.sharding.ViewShard: rows are sharded by view, K/V all-gathered per call
+
+    def partner_index(self, R, kv_index, device):
+        """int32 device index: row r reads K/V of row partner[p*R + r]
+        (swap halves, attention_processor.py:575-576, or gather, :578)."""
+        R_src = R if self.shard is None else R * self.shard.world   # rows of the (gathered) K/V buffer
+        if kv_index is None:
+            key = ("swap", R, device)
+            if key not in self._idx:
+                if self.shard is None:
+                    half = torch.cat([torch.arange(R // 2, R), torch.arange(0, R // 2)])
+                else:
+                    half = torch.from_numpy(self.shard.swap_halves_index(R_src))
+                self._idx[key] = half.to(device=device, dtype=torch.int32)
+            return self._idx[key]
+        if isinstance(kv_index, torch.Tensor):
+            idx = kv_index.to(device=device, dtype=torch.int32).contiguous()
+            host = None
+        else:
+            host = np.ascontiguousarray(np.asarray(kv_index, dtype=np.int64))
+            key = (host.tobytes(), R, device)
+            if key in self._idx:
+                return self._idx[key]
+            idx = torch.from_numpy(host.astype(np.int32)).to(device)
+        if idx.shape[0] % R != 0:
+            raise AssertionError("kv_index length must be a multiple of the row count (attention_processor.py:580)")
+        if host is not None:
+            if host.min() < 0 or host.max() >= R_src:
+                raise IndexError("kv_index out of range")
+            if len(self._idx) > 64:
+                self._idx.clear()
+            self._idx[key] = idx
+        return idx
+
+    def forward(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, kv_index=None, temb=None,
+                scale=None, mono_direction=False, fix_firstframe=False, epi_rowp=None, partner=None, **useless_kwargs):
+        assert hidden_states.ndim == 3   # BF x HW x C  (attention_processor.py:565)
+        if mono_direction:
+            raise ValueError("kv_index may have bug here. Not supported")   # attention_processor.py:621-622
+        if attention_mask is not None:
+            raise _lib.CvdError("a dense attention_mask is not accepted: the epipolar bias is generated in-kernel "
+                                "from the row table (epi_rowp)")
+        if encoder_hidden_states is not None:
+            raise _lib.CvdError("explicit encoder_hidden_states are not supported; pass kv_index")
+        _require_inference(attn, hidden_states)
+        R, N, C = hidden_states.shape
+        H = attn.heads
+        d = C // H
+        x = hidden_states if hidden_states.dtype == torch.bfloat16 else hidden_states.to(torch.bfloat16)
+        x = x.contiguous()
+        if partner is None:
+            partner = self.partner_index(R, kv_index, x.device)
+        w = attn._w
+        q = F.linear(x, w.bf16("q", attn.to_q.weight))
+        k = F.linear(x, w.bf16("k", attn.to_k.weight))
+        wv, bv = attn.padded_v_weights()
+        # V^T per head with a row of ones: [R, H*DV, N] = bias + Wv_pad @ x^T
+        vt = torch.baddbmm(bv, wv.unsqueeze(0).expand(R, -1, -1), x.transpose(1, 2)).view(R, H, ops.dv_rows(d), N)
+        k_src, vt_src = k, vt
+        if self.shard is not None:
+            # view sharding: partner rows live on other ranks -> one K / V^T all-gather per call;
+            # `partner` / kv_index then address rows of the gathered (global) buffers
+            k_src, vt_src = self.shard.gather_rows(k), self.shard.gather_rows(vt)
+        o = ops.epi_attn_fwd(q, k_src, vt_src, epi_rowp, partner, H, attn.F_mat_size)
+        if fix_firstframe:
+            # attention_processor.py:629-635: first-frame rows take the batch-mean self value
+            v_self = F.linear(x, w.bf16("v", attn.to_v.weight)).view(-1, 2, FRAMES_PER_VIDEO, N, C)
+            ff = v_self[:, :, 0].float().mean(dim=0, keepdim=True).to(o.dtype)
+            o.view(-1, 2, FRAMES_PER_VIDEO, N, C)[:, :, 0] = ff
+        y = F.linear(o, w.bf16("o", attn.to_out[0].weight))     # bias / rescale are applied by the caller
+        return y, {"query": q, "key": k}
+
+
+class EpiSelfAttention(nn.Module):
+    """epi_module.py:350-462 (diffusers ``Attention`` subclass in the reference).
+
+    ``forward(hidden_states[R,N,C], F_mats, H_mats, encoder_hidden_states, attention_mask, **kw)
+    -> (out[R,N,C], aux)`` with ``F_mats`` a tensor ``[R,3,3]`` or ``[tensor[k*R,3,3], kv_index]``.
+    ``aux = {"query", "key"}`` holds the un-split projections (bf16 here) or None in the
+    reference's memory-relief branch, whose semantics (``R > 200`` or ``M > 2048``: self-attention
+    for a tensor ``F_mats``, remainder rows dropped, epi_module.py:424-451) are reproduced when
+    ``reference_chunk_quirk`` is left on."""
+
+    def __init__(self, attention_mode=None, epi_position_encoding=False, epi_position_encoding_feat_max_size=32,
+                 epi_position_encoding_F_mat_size=256, epi_no_attention_mask=False, epi_mono_direction=False,
+                 epi_fix_firstframe=False, epi_rand_slope_ff=False, rescale_output_factor=1.0,
+                 query_dim=None, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
+                 upcast_attention=False, reference_chunk_quirk=True, **unused):
+        super().__init__()
+        assert attention_mode == "Epi_Self"
+        inner = heads * dim_head
+        self.heads = heads
+        self.inner_dim = inner
+        self.scale = dim_head ** -0.5
+        self.to_q = nn.Linear(query_dim, inner, bias=bias)
+        self.to_k = nn.Linear(cross_attention_dim or query_dim, inner, bias=bias)
+        self.to_v = nn.Linear(cross_attention_dim or query_dim, inner, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(dropout)])
+        if bias:
+            raise NotImplementedError("attention_bias=True is not on the reference path (epi_module.py:104)")
+        self.pos_encoder = EpiEncoding(query_dim, dropout=0., max_feat_size=epi_position_encoding_feat_max_size,
+                                       F_mat_size=epi_position_encoding_F_mat_size,
+                                       rand_slope_on_first_frame=epi_rand_slope_ff) if epi_position_encoding else None
+        self.F_mat_size = epi_position_encoding_F_mat_size
+        self.rescale_output_factor = rescale_output_factor
+        self.epi_no_attention_mask = epi_no_attention_mask
+        self.epi_mono_direction = epi_mono_direction
+        self.epi_fix_firstframe = epi_fix_firstframe
+        self.reference_chunk_quirk = reference_chunk_quirk
+        self.residual_connection = False
+        self.group_norm = None
+        self.processor = EpiAttnProcessor(hidden_size=query_dim)
+        self._w = _WeightCache()
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def set_use_memory_efficient_attention_xformers(self, *args, **kwargs):
+        pass   # epi_module.py:379-384
+
+    def padded_v_weights(self):
+        """to_v as the [H*DV, C] operand of the V^T GEMM (zero rows on the padding) and its
+        bias column [1, H*DV, 1] holding 1.0 on row ``d`` of every head."""
+        def make(wv):
+            H, C = self.heads, wv.shape[1]
+            d = wv.shape[0] // H
+            DV = ops.dv_rows(d)
+            wp = torch.zeros(H, DV, C, device=wv.device, dtype=torch.bfloat16)
+            wp[:, :d] = wv.detach().view(H, d, C).to(torch.bfloat16)
+            b = torch.zeros(H, DV, device=wv.device, dtype=torch.bfloat16)
+            b[:, d] = 1.0
+            return wp.view(H * DV, C).contiguous(), b.view(1, H * DV, 1).contiguous()
+        return self._w.get("v_pad", self.to_v.weight, make)
+
+    def attend(self, hidden_states, F_mats=None, H_mats=None, **kw):
+        """Core of forward: returns (y bf16 [R',N,C] *without* the to_out bias, aux)."""
+        if H_mats is not None:
+            raise NotImplementedError("the H_mats (homography) branch is training-only (epi_module.py:301-310) and is not built")
+        assert isinstance(self.processor, EpiAttnProcessor)   # epi_module.py:423
+        kw = {k: v for k, v in kw.items() if k not in ("pose_feature", "sync_lora_scale")}
+        scale = kw.pop("scale", None)
+        Fm, kv_index = (F_mats[0], F_mats[1]) if isinstance(F_mats, (list, tuple)) else (F_mats, None)
+        R, N, _ = hidden_states.shape
+        rowp = None
+        if self.pos_encoder is not None and not self.epi_no_attention_mask:
+            if Fm is None:
+                raise NotImplementedError("F_mats=None (random pseudo lines on every row, epi_module.py:317-320) is not built")
+            rowp = self.pos_encoder.row_params(hidden_states, Fm)
+            assert rowp.shape[0] % R == 0   # epi_module.py:399
+        n_partners = 1 if rowp is None else rowp.shape[0] // R
+        if self.reference_chunk_quirk and rowp is not None and (R > 200 or N * n_partners > 2048):
+            # epi_module.py:424-451: every chunk of `chunk` rows attends to encoder_hidden_states =
+            # hidden_states[kv_index] (list F_mats) or to ITSELF (tensor F_mats); rows past the last
+            # full chunk are dropped; aux is None.
+            chunk = 128 * 1024 // max(1024, N * n_partners)
+            keep = (R // chunk) * chunk
+            if kv_index is None:
+                src = torch.arange(R, device=hidden_states.device, dtype=torch.int32)
+            else:
+                src = self.processor.partner_index(R, kv_index, hidden_states.device)
+            if src.shape[0] != R:
+                raise IndexError("the reference's chunk branch indexes one partner per row")
+            y, _ = self.processor(self, hidden_states, kv_index=None, scale=scale, mono_direction=self.epi_mono_direction,
+                                  fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp[:R].contiguous(), partner=src, **kw)
+            return y[:keep], None
+        return self.processor(self, hidden_states, kv_index=kv_index, scale=scale, mono_direction=self.epi_mono_direction,
+                              fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp, **kw)
+
+    def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
+                **cross_attention_kwargs):
+        if attention_mask is not None or encoder_hidden_states is not None:
+            raise _lib.CvdError("EpiSelfAttention builds its own bias / partner rows; attention_mask and "
+                                "encoder_hidden_states must be None (as in every reference call site)")
+        y, aux = self.attend(hidden_states, F_mats, H_mats, **cross_attention_kwargs)
+        w = self._w
+        out = (y.float() + w.f32("bo", self.to_out[0].bias)) / self.rescale_output_factor
+        return out.to(hidden_states.dtype), aux
+
+
+class EpiTransformerBlock(nn.Module):
+    """epi_module.py:191-269."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, attention_block_types=("Epi_Self", "Epi_Self"),
+                 dropout=0.0, norm_num_groups=32, cross_attention_dim=768, activation_fn="geglu", attention_bias=False,
+                 upcast_attention=False, epi_position_encoding=False, epi_position_encoding_feat_max_size=32,
+                 epi_position_encoding_F_mat_size=256, epi_no_attention_mask=False, epi_mono_direction=False,
+                 epi_fix_firstframe=False, epi_rand_slope_ff=False, encoder_hidden_states_query=(False, False),
+                 attention_activation_scale=1.0, attention_processor_kwargs: Dict = {}, rescale_output_factor=1.0):
+        super().__init__()
+        self.attention_block_types = attention_block_types
+        self.attention_blocks = nn.ModuleList([
+            EpiSelfAttention(attention_mode=name, cross_attention_dim=None, query_dim=dim, heads=num_attention_heads,
+                             dim_head=attention_head_dim, dropout=dropout, bias=attention_bias,
+                             upcast_attention=upcast_attention, epi_position_encoding=epi_position_encoding,
+                             epi_position_encoding_feat_max_size=epi_position_encoding_feat_max_size,
+                             epi_position_encoding_F_mat_size=epi_position_encoding_F_mat_size,
+                             epi_no_attention_mask=epi_no_attention_mask, epi_mono_direction=epi_mono_direction,
+                             epi_fix_firstframe=epi_fix_firstframe, epi_rand_slope_ff=epi_rand_slope_ff,
+                             rescale_output_factor=rescale_output_factor)
+            for name in attention_block_types])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in attention_block_types])
+        self.ff = FeedForward(dim, dropout=dropout, activation_fn=activation_fn)
+        self.ff_norm = nn.LayerNorm(dim)
+        self._w = _WeightCache()
+
+    def forward_stream(self, hs, F_mats, H_mats=None, cross_attention_kwargs: Dict[str, Any] = {}, want_bf16=False):
+        """In-place update of the fp32 residual stream ``hs`` [R,N,C]; returns (hs, bf16 copy | None, aux)."""
+        w = self._w
+        aux_all = []
+        for i, (attn, norm) in enumerate(zip(self.attention_blocks, self.norms)):
+            n = ops.layernorm(hs, w.f32(f"g{i}", norm.weight), w.f32(f"b{i}", norm.bias), norm.eps)
+            y, aux = attn.attend(n, F_mats=F_mats, H_mats=H_mats, **cross_attention_kwargs)
+            if y.shape[0] != hs.shape[0]:
+                raise RuntimeError("the reference's chunk branch dropped rows; the residual add cannot broadcast "
+                                   "(the reference fails here too, epi_module.py:263)")
+            ops.residual_add_(hs, y, attn._w.f32("bo", attn.to_out[0].bias), 1.0 / attn.rescale_output_factor)
+            aux_all.append(aux)
+        n = ops.layernorm(hs, w.f32("gf", self.ff_norm.weight), w.f32("bf", self.ff_norm.bias), self.ff_norm.eps)
+        y = self.ff.forward_tokens(n)
+        hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
+        return hs, hb, aux_all
+
+    def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs: Dict[str, Any] = {}):
+        _require_inference(self, hidden_states)
+        hs = hidden_states.float().contiguous().clone()
+        hs, _, aux = self.forward_stream(hs, F_mats, H_mats, cross_attention_kwargs)
+        return hs.to(hidden_states.dtype), aux
+
+
+class EpiTransformer3DModel(nn.Module):
+    """epi_module.py:92-188."""
+
+    def __init__(self, in_channels, num_attention_heads, attention_head_dim, num_layers,
+                 attention_block_types=("Epi_Self",), dropout=0.0, norm_num_groups=32, cross_attention_dim=320,
+                 activation_fn="geglu", attention_bias=False, upcast_attention=False, epi_position_encoding=False,
+                 epi_position_encoding_feat_max_size=32, epi_position_encoding_F_mat_size=256,
+                 epi_no_attention_mask=False, epi_mono_direction=False, epi_fix_firstframe=False,
+                 epi_rand_slope_ff=False, encoder_hidden_states_query=(False, False), attention_activation_scale=1.0,
+                 attention_processor_kwargs: Dict = {}, rescale_output_factor=1.0):
+        super().__init__()
+        inner_dim = num_attention_heads * attention_head_dim
+        self.norm = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner_dim)
+        self.transformer_blocks = nn.ModuleList([
+            EpiTransformerBlock(dim=inner_dim, num_attention_heads=num_attention_heads,
+                                attention_head_dim=attention_head_dim, attention_block_types=attention_block_types,
+                                dropout=dropout, norm_num_groups=norm_num_groups, cross_attention_dim=cross_attention_dim,
+                                activation_fn=activation_fn, attention_bias=attention_bias,
+                                upcast_attention=upcast_attention, epi_position_encoding=epi_position_encoding,
+                                epi_position_encoding_feat_max_size=epi_position_encoding_feat_max_size,
+                                epi_position_encoding_F_mat_size=epi_position_encoding_F_mat_size,
+                                epi_no_attention_mask=epi_no_attention_mask, epi_mono_direction=epi_mono_direction,
+                                epi_fix_firstframe=epi_fix_firstframe, epi_rand_slope_ff=epi_rand_slope_ff,
+                                encoder_hidden_states_query=encoder_hidden_states_query,
+                                attention_activation_scale=attention_activation_scale,
+                                attention_processor_kwargs=attention_processor_kwargs,
+                                rescale_output_factor=rescale_output_factor)
+            for _ in range(num_layers)])
+        self.proj_out = nn.Linear(inner_dim, in_channels)
+        self._w = _WeightCache()
+
+    def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs: Dict[str, Any] = {}):
+        assert hidden_states.dim() == 5, f"Expected hidden_states to have ndim=5, but got ndim={hidden_states.dim()}."
+        _require_inference(self, hidden_states)
+        x = hidden_states.contiguous()
+        w = self._w
+        if F_mats is not None:   # epi_module.py:166-170
+            if isinstance(F_mats, torch.Tensor):
+                F_mats = F_mats.reshape(-1, 3, 3)
+            else:
+                F_mats = [F_mats[0].reshape(-1, 3, 3), F_mats[1]]
+        if H_mats is not None:
+            H_mats = H_mats.reshape(-1, 3, 3)
+        g = ops.groupnorm_tokens(x, w.f32("gn_w", self.norm.weight), w.f32("gn_b", self.norm.bias), self.norm.num_groups,
+                                 self.norm.eps, _lib.LAYOUT_BF_HW)
+        hs = F.linear(g, w.bf16("in_w", self.proj_in.weight), w.bf16("in_b", self.proj_in.bias)).float()
+        aux_all, hb = [], None
+        last = len(self.transformer_blocks) - 1
+        for i, block in enumerate(self.transformer_blocks):
+            hs, hb, aux = block.forward_stream(hs, F_mats, H_mats, cross_attention_kwargs, want_bf16=(i == last))
+            aux_all += aux
+        if hb is None:
+            hb = hs.to(torch.bfloat16)
+        t = F.linear(hb, w.bf16("out_w", self.proj_out.weight))
+        out = ops.tokens_to_video(t, w.f32("out_b", self.proj_out.bias), x, _lib.LAYOUT_BF_HW)
+        return out, aux_all
+
+
+class EpiModule(nn.Module):
+    """epi_module.py:38-89: ``forward(hidden_states[B,C,F,h,w], F_mats, H_mats, temb,
+    encoder_hidden_states, attention_mask, cross_attention_kwargs) -> (out, aux list)``."""
+
+    def __init__(self, in_channels, num_attention_heads=8, num_transformer_block=2, attention_block_types=("Epi_Self",),
+                 epi_position_encoding=True, epi_position_encoding_feat_max_size=64, epi_position_encoding_F_mat_size=256,
+                 epi_no_attention_mask=False, epi_mono_direction=False, epi_fix_firstframe=False, epi_rand_slope_ff=False,
+                 cross_attention_dim=320, zero_initialize=True, encoder_hidden_states_query=(False, False),
+                 attention_activation_scale=1.0, attention_processor_kwargs: Dict = {}, rescale_output_factor=1.0):
+        super().__init__()
+        self.epi_transformer = EpiTransformer3DModel(
+            in_channels=in_channels, num_attention_heads=num_attention_heads,
+            attention_head_dim=in_channels // num_attention_heads, num_layers=num_transformer_block,
+            attention_block_types=attention_block_types, cross_attention_dim=cross_attention_dim,
+            epi_position_encoding=epi_position_encoding,
+            epi_position_encoding_feat_max_size=epi_position_encoding_feat_max_size,
+            epi_position_encoding_F_mat_size=epi_position_encoding_F_mat_size,
+            epi_no_attention_mask=epi_no_attention_mask, epi_mono_direction=epi_mono_direction,
+            epi_fix_firstframe=epi_fix_firstframe, epi_rand_slope_ff=epi_rand_slope_ff,
+            encoder_hidden_states_query=encoder_hidden_states_query,
+            attention_activation_scale=attention_activation_scale,
+            attention_processor_kwargs=attention_processor_kwargs, rescale_output_factor=rescale_output_factor)
+        if zero_initialize:
+            self.epi_transformer.proj_out = zero_module(self.epi_transformer.proj_out)
+
+    def forward(self, hidden_states, F_mats=None, H_mats=None, temb=None, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs: Dict[str, Any] = {}):
+        return self.epi_transformer(hidden_states, F_mats, H_mats, encoder_hidden_states, attention_mask,
+                                    cross_attention_kwargs=cross_attention_kwargs)

@@ -1,0 +1,95 @@
+"""Host-side camera geometry feeding the epi module: pose files -> relative c2w / K ->
+per-frame-pair fundamental matrices.  Mirrors ``animatediff/data/dataset_validation.py``
+(calc_cross_product_matrix :28, calc_essential_matrix :45, calc_fundamental_matrix :57,
+Camera :79, ValRealEstate10KPoseFolded.load_cameras_specific/get_batch :180-271) and the
+per-UNet-call recompute of ``pipelines/pipeline_animation_epi_advanced.py:636-647``, which is
+batched here instead of a Python loop over V*16 frames.  fp64 numpy, like the reference.
+"""
+import numpy as np
+import torch
+
+
+def calc_cross_product_matrix(vec):
+    """[a]x for a 3-vector or an [N,3] array (dataset_validation.py:28-39)."""
+    v = np.asarray(vec, dtype=np.float64)
+    single = v.ndim == 1
+    v = v.reshape(-1, 3)
+    m = np.zeros((v.shape[0], 3, 3))
+    m[:, 0, 1], m[:, 0, 2], m[:, 1, 2] = -v[:, 2], v[:, 1], -v[:, 0]
+    m = m - m.transpose(0, 2, 1)
+    return m[0] if single else m
+
+
+def calc_essential_matrix(T_mat):
+    """E = R [(-R^T t)]x; accepts [4,4] or a batch [...,4,4] (dataset_validation.py:45-50)."""
+    T = np.asarray(T_mat, dtype=np.float64)
+    R, t = T[..., :3, :3], T[..., :3, 3]
+    t_ess = -np.einsum("...ji,...j->...i", R, t)
+    cross = calc_cross_product_matrix(t_ess.reshape(-1, 3)).reshape(R.shape)
+    return R @ cross
+
+
+def calc_fundamental_matrix(T_mat, K_mat1, K_mat2):
+    """F = K2^-T E K1^-1, batched over leading dims (dataset_validation.py:57-64)."""
+    E = calc_essential_matrix(T_mat)
+    K2_invT = np.swapaxes(np.linalg.inv(np.asarray(K_mat2, dtype=np.float64)), -1, -2)
+    K1_inv = np.linalg.inv(np.asarray(K_mat1, dtype=np.float64))
+    return K2_invT @ E @ K1_inv
+
+
+class Camera:
+    """One row of a RealEstate10K pose file (dataset_validation.py:79-91)."""
+
+    def __init__(self, entry):
+        self.cid = entry[0]
+        self.fx, self.fy, self.cx, self.cy = entry[1:5]
+        w2c = np.eye(4)
+        w2c[:3, :] = np.array(entry[7:]).reshape(3, 4)
+        self.w2c_mat = w2c
+        self.c2w_mat = np.linalg.inv(w2c)
+
+
+def read_pose_file(path):
+    with open(path, "r") as fh:
+        lines = fh.readlines()[1:]
+    return [Camera([float(x) for x in ln.strip().split(" ")]) for ln in lines if ln.strip()]
+
+
+def folded_pose_pair(pose_file_0, pose_file_1, sample_n_frames=16, sample_size=256):
+    """F_mats float32 [2n,3,3], c2w [2n-1,4,4], K [2n-1,3,3] of the folded two-trajectory layout
+    that inference_epi.py feeds the pipeline (dataset_validation.py:180-271, quirks included:
+    H,W = 1280,720; trajectory 1 reversed; K of trajectory 0 used for both)."""
+    cams0 = read_pose_file(pose_file_0)
+    cams1 = read_pose_file(pose_file_1)[::-1]
+    H, W = 1280, 720
+    crop = min(H, W)
+    rescale = sample_size / crop
+    dH, dW = (H - crop) / 2, (W - crop) / 2
+    K0 = np.array([[[W * rescale * c.fx, 0, (W * c.cx - dW) * rescale],
+                    [0, H * rescale * c.fy, (H * c.cy - dH) * rescale],
+                    [0, 0, 1]] for c in cams0])
+
+    def relative(cams):
+        inv0 = np.linalg.inv(cams[0].c2w_mat)
+        return np.array([inv0 @ c.c2w_mat for c in cams], dtype=np.float32)
+
+    c2w = np.concatenate([relative(cams0)[1:][::-1], relative(cams1)], axis=0)
+    K = np.concatenate([K0[1:][::-1], K0], axis=0)
+    n = sample_n_frames
+    sid = n - 1 - np.arange(n)
+    tid = n - 1 + np.arange(n)
+    s2t = np.linalg.inv(c2w[tid].astype(np.float64)) @ c2w[sid]
+    Fm = torch.as_tensor(calc_fundamental_matrix(s2t, K[sid], K[tid])).float()
+    return torch.cat([Fm, Fm.permute(0, 2, 1)], dim=0).contiguous(), c2w, K
+
+
+def pairwise_fundamental_matrices(c2w, K, video_id, n_frames=16):
+    """Per-UNet-call F for a view pairing (pipeline_animation_epi_advanced.py:636-647):
+    row (v, f) gets F of source (v, f) -> target (video_id[v], f).  c2w [V*n,4,4], K [V*n,3,3]."""
+    c2w = np.asarray(c2w, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    V = len(video_id)
+    src = np.arange(V * n_frames)
+    tgt = (np.asarray(video_id)[:, None] * n_frames + np.arange(n_frames)[None]).reshape(-1)
+    s2t = np.linalg.inv(c2w[tgt]) @ c2w[src]
+    return torch.as_tensor(calc_fundamental_matrix(s2t, K[src], K[tgt])).float()

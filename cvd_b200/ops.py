@@ -1,0 +1,188 @@
+"""Tensor-level wrappers over the C ABI (``include/cvd_b200.h``).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op below passes raw
+device pointers to ``libcvd_b200.so`` on ``torch.cuda.current_stream()``.  Inputs must be
+CUDA tensors -- there is no CPU path and nothing here ever imports ``oracle/``.
+"""
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16, torch.float16: _lib.DTYPE_F16}
+
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(t, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.CvdError(f"{name} must be a CUDA tensor (cvd_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise _lib.CvdError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.CvdError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def dv_rows(head_dim):
+    """Rows of one head of the transposed-V operand: d values, a row of ones, zero padding."""
+    return (head_dim // 16 + 1) * 16
+
+
+def epi_row_params(F_mats, feat, F_mat_size, theta=None, first_frame_rule=_lib.FF_HORIZONTAL,
+                   pixel_band=3.0, decay_alpha=3.0, frames_per_video=16):
+    """F_mats fp32 [rows,3,3] -> row table fp32 [rows,12] (EpiEncoding.get_attn_map prepass)."""
+    rows = F_mats.shape[0]
+    rowp = torch.empty(rows, _lib.ROWP_STRIDE, device=F_mats.device, dtype=torch.float32)
+    tp = None
+    if first_frame_rule == _lib.FF_RANDOM_SLOPE:
+        tp = _check(theta, torch.float32, "theta")
+    _lib.call("cvd_epi_row_params", _check(F_mats, torch.float32, "F_mats"), tp, rowp.data_ptr(), rows, feat,
+              float(F_mat_size), float(pixel_band), float(decay_alpha), first_frame_rule, frames_per_video, _stream())
+    _count()
+    return rowp
+
+
+def epi_bias_dense(rowp, feat, F_mat_size):
+    """Parity/debug only: dense bias [rows, N, N] fp32."""
+    rows, N = rowp.shape[0], feat * feat
+    bias = torch.empty(rows, N, N, device=rowp.device, dtype=torch.float32)
+    _lib.call("cvd_epi_bias_dense", _check(rowp, torch.float32, "rowp"), bias.data_ptr(), rows, feat,
+              float(F_mat_size), _stream())
+    _count()
+    return bias
+
+
+def _attn_args(q, k, vt, rowp, partner, heads):
+    R, N, C = q.shape
+    d = C // heads
+    R_kv = k.shape[0]
+    n_partners = partner.shape[0] // R
+    assert k.shape == (R_kv, N, C) and vt.shape == (R_kv, heads, dv_rows(d), N), (q.shape, k.shape, vt.shape)
+    assert partner.shape[0] == n_partners * R
+    feat = int(round(N ** 0.5))
+    return R, R_kv, N, d, n_partners, feat
+
+
+def epi_attn_fwd(q, k, vt, rowp, partner, heads, F_mat_size, dbg_s=None):
+    """tcgen05 fused epipolar attention.  q,k bf16 [R,N,C]; vt bf16 [R,H,DV,N]; -> bf16 [R,N,C]."""
+    R, R_kv, N, d, n_partners, feat = _attn_args(q, k, vt, rowp, partner, heads)
+    out = torch.empty_like(q)
+    rp = None if rowp is None else _check(rowp, torch.float32, "rowp")
+    args = [_check(q, torch.bfloat16, "q"), _check(k, torch.bfloat16, "k"), _check(vt, torch.bfloat16, "vt"), rp,
+            _check(partner, torch.int32, "partner"), out.data_ptr()]
+    tail = [R, R_kv, N, heads, d, n_partners, feat, float(F_mat_size), _stream()]
+    if dbg_s is None:
+        _lib.call("cvd_epi_attn_fwd", *args, *tail)
+    else:
+        _lib.call("cvd_epi_attn_fwd_debug", *args, _check(dbg_s, torch.float32, "dbg_s"), *tail)
+    _count()
+    return out
+
+
+def epi_attn_fwd_simt(q, k, vt, rowp, partner, heads, F_mat_size, out_dtype=torch.float32):
+    """CUDA-core cross-check of :func:`epi_attn_fwd` (tests only)."""
+    R, R_kv, N, d, n_partners, feat = _attn_args(q, k, vt, rowp, partner, heads)
+    out = torch.empty(q.shape, device=q.device, dtype=out_dtype)
+    rp = None if rowp is None else _check(rowp, torch.float32, "rowp")
+    _lib.call("cvd_epi_attn_fwd_simt", _check(q, torch.bfloat16, "q"), _check(k, torch.bfloat16, "k"),
+              _check(vt, torch.bfloat16, "vt"), rp, _check(partner, torch.int32, "partner"), out.data_ptr(),
+              _DT[out_dtype], R, R_kv, N, heads, d, n_partners, feat, float(F_mat_size), _stream())
+    _count()
+    return out
+
+
+def groupnorm_tokens(x, gamma, beta, groups=32, eps=1e-6, layout=_lib.LAYOUT_BF_HW):
+    """x [B,C,F,h,w] -> bf16 tokens ([B*F, h*w, C] or [B*h*w, F, C])."""
+    B, C, Fr, h, w = x.shape
+    HW = h * w
+    shape = (B * Fr, HW, C) if layout == _lib.LAYOUT_BF_HW else (B * HW, Fr, C)
+    y = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty(B * Fr * groups * 2, device=x.device, dtype=torch.float32)
+    _lib.call("cvd_groupnorm_tokens_fwd", _check(x, None, "x"), _DT[x.dtype], _check(gamma, torch.float32, "gamma"),
+              _check(beta, torch.float32, "beta"), y.data_ptr(), stats.data_ptr(), B, C, Fr, HW, groups, float(eps),
+              layout, _stream())
+    _count(2)
+    return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5, pe=None, seq_len=1):
+    """fp32 tokens [..., C] -> bf16, optional positional table pe[seq_len, C] added after the norm."""
+    C = x.shape[-1]
+    tokens = x.numel() // C
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("cvd_layernorm_fwd", _check(x, torch.float32, "x"), _check(gamma, torch.float32, "gamma"),
+              _check(beta, torch.float32, "beta"), None if pe is None else _check(pe, torch.float32, "pe"),
+              y.data_ptr(), tokens, C, seq_len, float(eps), _stream())
+    _count()
+    return y
+
+
+def geglu(hg):
+    """bf16 [..., 2*inner] -> bf16 [..., inner]: h * gelu_erf(g)."""
+    inner = hg.shape[-1] // 2
+    tokens = hg.numel() // hg.shape[-1]
+    out = torch.empty(*hg.shape[:-1], inner, device=hg.device, dtype=torch.bfloat16)
+    _lib.call("cvd_geglu_fwd", _check(hg, torch.bfloat16, "hg"), out.data_ptr(), tokens, inner, _stream())
+    _count()
+    return out
+
+
+def residual_add_(x, y, bias=None, scale=1.0, want_bf16=False):
+    """x (fp32, in place) += (y (bf16) + bias) * scale; optionally also returns a bf16 copy."""
+    C = x.shape[-1]
+    tokens = x.numel() // C
+    xb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    _lib.call("cvd_residual_add_fwd", _check(x, torch.float32, "x"), _check(y, torch.bfloat16, "y"),
+              None if bias is None else _check(bias, torch.float32, "bias"), float(scale),
+              None if xb is None else xb.data_ptr(), tokens, C, _stream())
+    _count()
+    return xb
+
+
+def tokens_to_video(tok, bias, residual, layout=_lib.LAYOUT_BF_HW):
+    """bf16 tokens (+bias) -> [B,C,F,h,w] in residual's dtype, plus the residual."""
+    B, C, Fr, h, w = residual.shape
+    out = torch.empty_like(residual)
+    _lib.call("cvd_tokens_to_video_fwd", _check(tok, torch.bfloat16, "tok"),
+              None if bias is None else _check(bias, torch.float32, "bias"), _check(residual, None, "residual"),
+              out.data_ptr(), _DT[residual.dtype], B, C, Fr, h * w, layout, _stream())
+    _count()
+    return out
+
+
+def temporal_attn(q, k, v, heads):
+    """bf16 [T, F, C] x3 -> bf16 [T, F, C]: per-pixel attention over the F frames."""
+    T, Fr, C = q.shape
+    out = torch.empty_like(q)
+    _lib.call("cvd_temporal_attn_fwd", _check(q, torch.bfloat16, "q"), _check(k, torch.bfloat16, "k"),
+              _check(v, torch.bfloat16, "v"), out.data_ptr(), T, Fr, heads, C // heads, _stream())
+    _count()
+    return out
+
+
+def add_pose_tokens(x_tok, pose):
+    """x_tok bf16 [(b h w), F, C] + pose [B,C,F,h,w] -> bf16 tokens."""
+    B, C, Fr, h, w = pose.shape
+    out = torch.empty_like(x_tok)
+    _lib.call("cvd_add_pose_tokens_fwd", _check(x_tok, torch.bfloat16, "x_tok"), _check(pose, None, "pose"),
+              _DT[pose.dtype], out.data_ptr(), B, C, Fr, h * w, _stream())
+    _count()
+    return out
+
+
+def scale_add(a, b, scale):
+    """bf16: a * scale + b."""
+    out = torch.empty_like(a)
+    _lib.call("cvd_scale_add_fwd", _check(a, torch.bfloat16, "a"), _check(b, torch.bfloat16, "b"), float(scale),
+              out.data_ptr(), a.numel(), _stream())
+    _count()
+    return out

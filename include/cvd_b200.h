@@ -1,0 +1,146 @@
+/*
+ * cvd_b200 -- C ABI of the B200-native CVD cross-video synchronisation hot path.
+ *
+ * The reference (JimmyPang02/CVD) is pure Python/PyTorch and has no FFI of its own; the
+ * entry points below are what a binding for this path would call, one per stage of the
+ * reference's EpiModule / VanillaTemporalModule forward.  Each declaration cites the
+ * reference lines it replaces (paths relative to the reference checkout).  The ctypes
+ * binding the Python host side uses is cvd_b200/_lib.py; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates inputs,
+ *     outputs and workspaces); the library never allocates or frees caller memory and
+ *     keeps no state besides per-process kernel attributes;
+ *   - all tensors are dense row-major; "bf16" buffers are passed as const void*;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream); every call is
+ *     asynchronous and stream-ordered, no call synchronises the device;
+ *   - return value 0 = success, negative = error (CVD_E_*); cvd_last_error() returns a
+ *     thread-local message.  Unsupported shapes are errors -- there is no fallback path.
+ */
+#ifndef CVD_B200_H_
+#define CVD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVD_OK 0
+#define CVD_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define CVD_E_CUDA (-2)      /* CUDA runtime or driver error      */
+
+#define CVD_DTYPE_F32 0
+#define CVD_DTYPE_BF16 1
+#define CVD_DTYPE_F16 2
+
+/* token layouts of a [B,C,F,h,w] video tensor */
+#define CVD_LAYOUT_BF_HW 0   /* "(b f) (h w) c"  -- epi module,      epi_module.py:165    */
+#define CVD_LAYOUT_BHW_F 1   /* "(b h w) f c"    -- temporal module, motion_module.py:378 */
+
+/* first-frame rule of the epipolar bias (epi_module.py:316,331-346) */
+#define CVD_FF_NONE 0        /* use F_r on every row (not reachable in the reference)   */
+#define CVD_FF_HORIZONTAL 1  /* rows r % frames == 0: line (0,-1,y_q)                    */
+#define CVD_FF_RANDOM_SLOPE 2/* rows r % frames == 0: line through q with slope *theta   */
+
+#define CVD_ROWP_STRIDE 12   /* floats per row of the row-parameter table               */
+
+typedef void* cvd_stream_t;
+
+const char* cvd_last_error(void);
+int cvd_abi_version(void);
+
+/* ---- a1/a2: epipolar bias, EpiEncoding.get_attn_map (epi_module.py:293-329) + NaN scrub
+ *      (epi_module.py:404-407).  The dense [rows,N,N] tensor is never built on the product
+ *      path: this prepass reduces each row's geometry to 12 floats
+ *        rowp[r] = { M00..M22 (effective line matrix, l_q = M x_q), band_r, w_r, 0 }
+ *      band_r = pixel_band/(S//2) * max_{q,k} d,  w_r = decay_alpha/(band_r+1e-6).
+ *      `theta` is a device scalar (radians) used when first_frame_rule == RANDOM_SLOPE. */
+int cvd_epi_row_params(const float* F_mats, const float* theta, float* rowp, int rows, int feat,
+                       float F_mat_size, float pixel_band, float decay_alpha,
+                       int first_frame_rule, int frames_per_video, cvd_stream_t stream);
+
+/* Parity/debug only: materialise bias[rows, N, N] (fp32) from the row parameters. */
+int cvd_epi_bias_dense(const float* rowp, float* bias, int rows, int feat, float F_mat_size,
+                       cvd_stream_t stream);
+
+/* ---- a4/a5: EpiAttnProcessor core (attention_processor.py:573-619,637):
+ *        out[r,n,h*d:(h+1)*d] = softmax_k( q.k/sqrt(d) + bias[r,n,k] ) v
+ *      with K/V taken from row partner[p*R + r] and bias row p*R + r for partner
+ *      p < n_partners (keys of all partners form one softmax, attention_processor.py:579-583).
+ *        q    : bf16 [R, N, heads*head_dim]
+ *        k    : bf16 [R_kv, N, heads*head_dim]   R_kv >= R when K/V were gathered from other
+ *               ranks (view sharding): partner[] then holds rows of the gathered buffer
+ *        vt   : bf16 [R_kv, heads, DV, N], DV = (head_dim/16 + 1)*16: V transposed per head; row
+ *               head_dim must be 1.0 and the rows above it 0 (the kernel reads the softmax
+ *               denominator from that row)
+ *        rowp : fp32 [n_partners*R, 12] from cvd_epi_row_params, or NULL for no bias
+ *               (epi_no_attention_mask, epi_module.py:392)
+ *        partner : int32 [n_partners*R]
+ *        out  : bf16 [R, N, heads*head_dim]
+ *      tcgen05/TMEM/TMA kernel; head_dim in {40, 80, 160}, N = feat*feat, feat in {4,8,16,32,64}. */
+int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, const float* rowp,
+                     const int* partner, void* out, int R, int R_kv, int N, int heads, int head_dim,
+                     int n_partners, int feat, float F_mat_size, cvd_stream_t stream);
+
+/* Bring-up aid: as cvd_epi_attn_fwd, and additionally dumps the raw Q K^T accumulator of key
+ * tile 0 of every CTA into dbg_s (fp32 [R*heads*ceil(N/128), 128, 64]). */
+int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const float* rowp,
+                           const int* partner, void* out, float* dbg_s, int R, int R_kv, int N,
+                           int heads, int head_dim, int n_partners, int feat, float F_mat_size,
+                           cvd_stream_t stream);
+
+/* Same contract (out may be bf16 or fp32), plain CUDA-core fp32 kernel that follows the
+ * reference's arithmetic literally (natural-log softmax, unrounded probabilities): the
+ * on-device cross-check used by the tests at sizes where the CPU oracle is slow.  Any
+ * head_dim <= 160.  Never called by the product path. */
+int cvd_epi_attn_fwd_simt(const void* q, const void* k, const void* vt, const float* rowp,
+                          const int* partner, void* out, int out_dtype, int R, int R_kv, int N,
+                          int heads, int head_dim, int n_partners, int feat, float F_mat_size,
+                          cvd_stream_t stream);
+
+/* ---- a7/a10: InflatedGroupNorm + rearrange to tokens (resnet.py:30-40, epi_module.py:163-165,
+ *      motion_module.py:377-378).  x [B,C,F,HW] (x_dtype) -> y bf16 tokens in `layout`.
+ *      stats: fp32 workspace [B*F*groups*2]. */
+int cvd_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, const float* beta,
+                             void* y, float* stats, int B, int C, int F, int HW, int groups,
+                             float eps, int layout, cvd_stream_t stream);
+
+/* ---- a6: LayerNorm over C of fp32 tokens -> bf16 (epi_module.py:254,266; motion_module.py:449,457).
+ *      Optional pe[seq_len, C] is added after the norm (PositionalEncoding, motion_module.py:479-481)
+ *      with position = token % seq_len. */
+int cvd_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* pe,
+                      void* y, int tokens, int C, int seq_len, float eps, cvd_stream_t stream);
+
+/* ---- a6: GEGLU gate (diffusers FeedForward used at epi_module.py:248):
+ *      out[t, i] = hg[t, i] * gelu_erf(hg[t, inner + i]),  hg bf16 [T, 2*inner] -> out bf16 [T, inner] */
+int cvd_geglu_fwd(const void* hg, void* out, int tokens, int inner, cvd_stream_t stream);
+
+/* ---- residual stream update: x[t,c] += (y[t,c] + bias[c]) * scale, x fp32 in place, y bf16;
+ *      optional bf16 copy of the result (input of the next GEMM).  (epi_module.py:263,266;
+ *      attention_processor.py:641-648: bias = to_out bias, scale = 1/rescale_output_factor) */
+int cvd_residual_add_fwd(float* x, const void* y, const float* bias, float scale, void* x_bf16,
+                         int tokens, int C, cvd_stream_t stream);
+
+/* ---- a7: proj_out epilogue: tokens -> "b c f h w" + residual (epi_module.py:185-187,
+ *      motion_module.py:390-392).  out = residual + transpose(tok + bias). */
+int cvd_tokens_to_video_fwd(const void* tok, const float* bias, const void* residual, void* out,
+                            int io_dtype, int B, int C, int F, int HW, int layout,
+                            cvd_stream_t stream);
+
+/* ---- a9: temporal self-attention over the F frames of every pixel
+ *      (attention_processor.py:84-94 / :346-357).  q,k,v,out bf16 [T, F, heads*head_dim], F <= 32. */
+int cvd_temporal_attn_fwd(const void* q, const void* k, const void* v, void* out, int T, int F,
+                          int heads, int head_dim, cvd_stream_t stream);
+
+/* ---- a9: CameraCtrl pose merge epilogue (attention_processor.py:324-326):
+ *      out = merged * scale + x,  merged = qkv_merge(x + pose) computed by the caller's GEMM.
+ *      x_plus_pose helper: out_bf16 = x_bf16 + pose (pose in video layout [B,C,F,HW], x tokens "(b h w) f c"). */
+int cvd_add_pose_tokens_fwd(const void* x_tok, const void* pose, int pose_dtype, void* out_tok,
+                            int B, int C, int F, int HW, cvd_stream_t stream);
+int cvd_scale_add_fwd(const void* a, const void* b, float scale, void* out, long long n,
+                      cvd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVD_B200_H_ */

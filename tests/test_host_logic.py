@@ -1,0 +1,101 @@
+"""CPU: host-side logic of the drop-in layers -- parameter names, partner-row resolution,
+geometry, error behaviour.  No kernels run."""
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+
+
+def test_state_dict_keys_match_the_reference():
+    """the keys cvd.ckpt['unet_trainable_dict'] carries."""
+    import cvd_b200
+    m = cvd_b200.get_epi_module(320, dict(num_attention_heads=8, num_transformer_block=1,
+                                          attention_block_types=["Epi_Self", "Epi_Self"],
+                                          epi_position_encoding_feat_max_size=64))
+    keys = set(m.state_dict().keys())
+    blk = "epi_transformer.transformer_blocks.0."
+    expect = {"epi_transformer.norm.weight", "epi_transformer.norm.bias", "epi_transformer.proj_in.weight",
+              "epi_transformer.proj_in.bias", "epi_transformer.proj_out.weight", "epi_transformer.proj_out.bias",
+              blk + "ff.net.0.proj.weight", blk + "ff.net.0.proj.bias", blk + "ff.net.2.weight", blk + "ff.net.2.bias",
+              blk + "ff_norm.weight", blk + "ff_norm.bias"}
+    for i in (0, 1):
+        expect |= {f"{blk}attention_blocks.{i}.{n}" for n in
+                   ("to_q.weight", "to_k.weight", "to_v.weight", "to_out.0.weight", "to_out.0.bias", "pos_encoder.coords")}
+        expect |= {f"{blk}norms.{i}.weight", f"{blk}norms.{i}.bias"}
+    assert keys == expect
+    assert sum(p.numel() for p in m.parameters()) == 2259520
+    assert m.state_dict()[blk + "attention_blocks.0.pos_encoder.coords"].shape == (64, 64, 3)
+    assert float(m.epi_transformer.proj_out.weight.abs().sum()) == 0.0      # zero_initialize
+    # the fixture state dicts (reference names) load with nothing unexpected
+    missing, unexpected = m.load_state_dict(gi.module_state_dict(320, 1), strict=False)
+    assert not unexpected and all("pos_encoder" in k for k in missing)
+
+
+def test_temporal_state_dict_keys():
+    import cvd_b200
+    m = cvd_b200.get_motion_module(320, "Vanilla", dict(num_attention_heads=8, num_transformer_block=1,
+                                                        attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                                        temporal_position_encoding=True,
+                                                        temporal_position_encoding_max_len=32, zero_initialize=False))
+    blk = m.temporal_transformer.transformer_blocks[0]
+    blk.attention_blocks[0].set_processor(cvd_b200.PoseAdaptorAttnProcessor(
+        hidden_size=320, pose_feature_dim=320, query_condition=True, key_value_condition=True))
+    missing, unexpected = m.load_state_dict(gi.temporal_state_dict(320, 1), strict=False)
+    assert not unexpected and all("pos_encoder" in k for k in missing)
+    p = "temporal_transformer.transformer_blocks.0.attention_blocks.0."
+    assert p + "processor.qkv_merge.weight" in m.state_dict() and p + "pos_encoder.pe" in m.state_dict()
+    from oracle import epi_oracle as O
+    assert torch.allclose(m.state_dict()[p + "pos_encoder.pe"][0], O.sinusoidal_pe(320, 32))
+
+
+def test_partner_index_resolution():
+    import cvd_b200
+    proc = cvd_b200.EpiAttnProcessor(hidden_size=320)
+    cpu = torch.device("cpu")
+    assert proc.partner_index(8, None, cpu).tolist() == [4, 5, 6, 7, 0, 1, 2, 3]       # swap halves
+    kv = gi.view_pair_index(4)                                                          # numpy int64, like the sampler's
+    idx = proc.partner_index(64, kv, cpu)
+    assert idx.dtype == torch.int32 and idx.tolist() == kv.tolist()
+    assert proc.partner_index(64, kv, cpu) is idx                                       # cached
+    assert proc.partner_index(64, torch.from_numpy(kv), cpu).tolist() == kv.tolist()
+    multi = np.concatenate([kv, np.arange(64)])
+    assert proc.partner_index(64, multi, cpu).shape[0] == 128
+    with pytest.raises(AssertionError):
+        proc.partner_index(64, np.arange(65), cpu)
+    with pytest.raises(IndexError):
+        proc.partner_index(64, np.arange(64) + 1, cpu)
+
+
+def test_reference_error_behaviour_without_gpu():
+    import cvd_b200
+    attn = cvd_b200.EpiSelfAttention(attention_mode="Epi_Self", query_dim=320, heads=8, dim_head=40,
+                                     epi_position_encoding=True, epi_mono_direction=True).eval()
+    x = torch.zeros(32, 16, 320)
+    with torch.no_grad():
+        with pytest.raises(cvd_b200.CvdError):          # no CPU path: loud failure, not a fallback
+            attn(x, F_mats=torch.zeros(32, 3, 3))
+    with pytest.raises(AssertionError):
+        cvd_b200.EpiSelfAttention(attention_mode="Temporal_Self", query_dim=320)
+    with pytest.raises(ValueError):                     # non-square latent (epi_module.py:294)
+        with torch.no_grad():
+            attn(torch.zeros(32, 15, 320), F_mats=torch.zeros(32, 3, 3))
+
+
+def test_geometry_matches_reference_fixture(golden):
+    from cvd_b200 import geometry as G
+    g = golden["geometry"]
+    Fm = G.pairwise_fundamental_matrices(g["c2w"][0], g["K_mats"], [1, 0])
+    np.testing.assert_allclose(Fm.numpy(), g["F_mats"], rtol=2e-4, atol=1e-9)
+    # batched implementation == the oracle's frame-by-frame loop for a 4-view pairing
+    from oracle import epi_oracle as O
+    rng = np.random.RandomState(3)
+    from scipy.spatial.transform import Rotation
+    c2w = np.tile(np.eye(4), (64, 1, 1))
+    c2w[:, :3, :3] = Rotation.from_rotvec(rng.randn(64, 3) * 0.2).as_matrix()
+    c2w[:, :3, 3] = rng.randn(64, 3)
+    K = np.tile(np.array([[223.578, 0, 128], [0, 223.578, 128], [0, 0, 1.0]]), (64, 1, 1))
+    pairing = [2, 3, 0, 1]
+    np.testing.assert_allclose(G.pairwise_fundamental_matrices(c2w, K, pairing).numpy(),
+                               O.pairwise_F_mats(c2w, K, pairing).numpy(), rtol=1e-5, atol=1e-9)
+    assert np.allclose(G.calc_cross_product_matrix(np.array([1.0, 2.0, 3.0])), O.cross_product_matrix([1, 2, 3]))
