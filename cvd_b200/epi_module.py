@@ -130,6 +130,25 @@ class EpiEncoding(nn.Module):
         return ops.epi_bias_dense(self.row_params(x, F_mats, pixel_band, decay_alpha), feat, self.F_mat_size)
 
 
+class _Aux(dict):
+    """``{"query", "key"}`` of EpiAttnProcessor (attention_processor.py:595-596,650).  The
+    reference's "key" is to_k of the PARTNER rows (multi-partner: interleaved along the keys,
+    :579-583); that gather is only materialised if somebody reads it (nothing at inference does)."""
+
+    def __init__(self, q, k, partner):
+        super().__init__(query=q, key=None)
+        self._k, self._partner = k, partner
+
+    def __getitem__(self, name):
+        if name == "key" and super().__getitem__("key") is None:
+            R, N, C = self["query"].shape
+            kk = self._k[self._partner.long()]
+            if kk.shape[0] != R:
+                kk = kk.reshape(-1, R, N, C).permute(1, 2, 0, 3).reshape(R, -1, C)
+            self["key"] = kk
+        return super().__getitem__(name)
+
+
 class EpiAttnProcessor(nn.Module):
     """attention_processor.py:522-650.  Parameter-free; installed with ``attn.set_processor``
     (``unet.set_all_attn_processor``) exactly like the reference's.  It receives the row table
@@ -210,7 +229,7 @@ class EpiAttnProcessor(nn.Module):
             ff = v_self[:, :, 0].float().mean(dim=0, keepdim=True).to(o.dtype)
             o.view(-1, 2, FRAMES_PER_VIDEO, N, C)[:, :, 0] = ff
         y = F.linear(o, w.bf16("o", attn.to_out[0].weight))     # bias / rescale are applied by the caller
-        return y, {"query": q, "key": k}
+        return y, _Aux(q, k_src, partner)
 
 
 class EpiSelfAttention(nn.Module):

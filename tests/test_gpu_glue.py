@@ -54,7 +54,9 @@ def test_geglu_and_residual(dev):
     hg = torch.randn(50, 16, 2560, generator=g).to(dev).to(torch.bfloat16)
     y = ops.geglu(hg)
     h, gate = hg.float().chunk(2, dim=-1)
-    assert_close(y, h * F.gelu(gate), rel=4e-3, max_abs=3e-2, what="geglu")
+    ref = h * F.gelu(gate)
+    assert_close(y, ref, rel=4e-3, max_abs=1.0, what="geglu")
+    assert torch.allclose(y.float(), ref, rtol=1e-2, atol=2e-3)      # bf16 output: error scales with |value|
     x = torch.randn(50, 16, 320, generator=g).to(dev)
     yb = torch.randn(50, 16, 320, generator=g).to(dev).to(torch.bfloat16)
     bias = torch.randn(320, generator=g).to(dev)

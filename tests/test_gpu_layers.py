@@ -50,6 +50,7 @@ def test_epi_self_attention_vs_reference_fixture(golden, dev, case):
     assert y.dtype == x.dtype and y.shape == x.shape
     assert_close(gi.stored(case, y), t(g[name + "_out"]), rel=REL, what=name)
     assert set(aux.keys()) == {"query", "key"} and aux["query"].shape == (R, feat * feat, C)
+    assert abs(float(aux["query"].double().abs().sum()) / float(g[name + "_qsum"]) - 1) < 5e-3
     assert abs(float(aux["key"].double().abs().sum()) / float(g[name + "_ksum"]) - 1) < 5e-3
     assert_close(aux["key"][0, ::case.get("queries", 1)], t(g[name + "_key0"]), rel=1e-2, what=name + " key")
 
@@ -140,7 +141,7 @@ def test_epi_module_vs_reference_fixture(golden, dev, case):
     assert len(aux) == int(g[name + "_naux"])
     ref = t(g[name + "_out"])
     assert_close(y, ref, rel=REL, what=name)
-    assert_close(y - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
+    assert_close(y.cpu() - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
 
 
 def test_epi_module_zero_init_is_identity(golden, dev):
@@ -171,7 +172,7 @@ def test_epi_module_res1_vs_oracle(golden, dev):
                      epi_position_encoding_F_mat_size=256, epi_rand_slope_ff=False, zero_initialize=True)
     with torch.no_grad():
         y, _ = m(x.to(dev), F_mats=Fm.to(dev))
-    assert_close(y - x.to(dev), ref - x, rel=3e-2, what="res-1 module delta")
+    assert_close(y.cpu() - x, ref - x, rel=3e-2, what="res-1 module delta")
 
 
 @pytest.mark.parametrize("case", gi.TEMPORAL_CASES, ids=lambda c: c["name"])
@@ -196,7 +197,7 @@ def test_temporal_module_vs_reference_fixture(golden, dev, case):
         y = m(x, cross_attention_kwargs={"pose_feature": pose})
     ref = t(g[name + "_out"])
     assert_close(y, ref, rel=REL, what=name)
-    assert_close(y - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
+    assert_close(y.cpu() - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
 
 
 def test_training_mode_is_refused(dev):
