@@ -55,7 +55,7 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-template <int D, int FEAT>
+template <int D, int FEAT, bool DBG>
 __global__ void __launch_bounds__(kThreads, Cfg<D>::kMinBlocks)
 epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
@@ -195,10 +195,13 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_proxy_async_smem();
     mbar_arrive(smem_u32(&bars->q_ready));
 
-    float As = 0.f, Bs = 0.f, base = 0.f, bandp = 0.f;   // t(key) = As*col + Bs*row + base  (base-2 units)
-    float m_used = -INFINITY;
+    // bias geometry of this thread's query pixel, base-2 units (already scaled by w_r * log2e / |l_q|):
+    //   t(key) = As * col + Bs * row + base,   bias = min(band' - |t|, 0) = min(band' - t, band' + t, 0)
+    float As = 0.f, Bs = 0.f, base = 0.f, bandp = 0.f;
+    float m_used = 0.f;                   // running reference maximum (0 until the first tile sets it)
     uint32_t sreg[kBlockN];
     uint32_t preg[kBlockN / 2];
+    const uint64_t scale2 = pack2(scale_log2, scale_log2);
 
     for (int it = 0; it < total; ++it) {
       const int p = it / kTilesPerPartner, j = it % kTilesPerPartner;
@@ -217,51 +220,65 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       const int buf = it & 1;
+      // DBG build: clock64 stamps of thread 0 at the hand-off points of every iteration, written
+      // behind the S dump: int64 [grid, 32, 8]
+      long long* stamps = nullptr;
+      if (DBG && tid == 0 && it < 32)
+        stamps = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kBlockN) + ((size_t)blockIdx.x * 32 + it) * 8;
+      if (DBG && stamps) stamps[0] = clock64();
       mbar_wait(smem_u32(&bars->s_full[buf]), (it >> 1) & 1);
       tc_fence_after();
+      if (DBG && stamps) stamps[1] = clock64();
       tmem_ld_x32(tlane + C::kColS + buf * kBlockN, sreg);
       tmem_ld_x32(tlane + C::kColS + buf * kBlockN + 32, sreg + 32);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->s_free[buf]));
+      if (DBG && stamps) stamps[2] = clock64();
 
-      if (dbg != nullptr && it == 0) {
+      if (DBG && it == 0) {
         float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kBlockN;
 #pragma unroll
         for (int c = 0; c < kBlockN; ++c) o[c] = __uint_as_float(sreg[c]);
       }
 
-      // scores in base-2 units: s = qk * log2e/sqrt(d) + min(band' - |t|, 0)
-      float rowbase[kRowsPerTile];
-#pragma unroll
-      for (int i = 0; i < kRowsPerTile; ++i) rowbase[i] = fmaf(Bs, (float)(j * kRowsPerTile + i), base);
-      float cmax = -INFINITY;
+      // x = qk * log2e/sqrt(d) + bias - m_used, evaluated against the CURRENT reference maximum so
+      // the subtraction is free: min(band'-m - t, band'-m + t, -m) is one FMNMX3, the two linear
+      // terms advance by one packed FADD2 per key pair, and the score is one packed FFMA2.
+      const float bm = bandp - m_used, negm = -m_used;
+      const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
+      float xmax = -INFINITY;
+      uint64_t a1 = 0, a2 = 0;
 #pragma unroll
       for (int c = 0; c < kBlockN; c += 2) {
-        float s2[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int cc = c + e;
-          const float t = fmaf(As, (float)(cc % FEAT), rowbase[cc / FEAT]);
-          const float v = fminf(bandp - fabsf(t), 0.f);
-          float s = fmaf(__uint_as_float(sreg[cc]), scale_log2, v);
-          if (N < kBlockN && cc >= N) s = -INFINITY;   // keys past the row (N = 16): not part of the softmax
-          s2[e] = s;
-          sreg[cc] = __float_as_uint(s);
+        if (c % FEAT == 0) {   // start of a key-grid row inside the tile
+          const float rb = fmaf(Bs, (float)(j * kRowsPerTile + c / FEAT), base);
+          a1 = pack2(bm - rb, bm - rb - As);
+          a2 = pack2(bm + rb, bm + rb + As);
         }
-        cmax = max3(cmax, s2[0], s2[1]);
+        float a1x, a1y, a2x, a2y;
+        unpack2(a1, a1x, a1y);
+        unpack2(a2, a2x, a2y);
+        const float v0 = min3(a1x, a2x, negm), v1 = min3(a1y, a2y, negm);
+        float x0, x1;
+        unpack2(fma2(pack2(__uint_as_float(sreg[c]), __uint_as_float(sreg[c + 1])), scale2, pack2(v0, v1)), x0, x1);
+        if (N < kBlockN && c >= N) x0 = x1 = -INFINITY;   // keys past the row (N = 16): not part of the softmax
+        xmax = max3(xmax, x0, x1);
+        sreg[c] = __float_as_uint(x0);
+        sreg[c + 1] = __float_as_uint(x1);
+        a1 = add2(a1, step1);
+        a2 = add2(a2, step2);
       }
 
-      if (it == 0) {
-        m_used = cmax;
-      } else {
-        const bool need = cmax > m_used + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // PV(it-1) must have landed in O before it is rescaled
-          mbar_wait(smem_u32(&bars->o_done), (it - 1) & 1);
+      if (DBG && stamps) stamps[3] = clock64() + (long long)(__float_as_uint(xmax) & 1u);
+      // lazy maximum update: only when this tile exceeds the reference by more than 2^8 (or on the
+      // very first tile) is the reference moved, O rescaled and x shifted.
+      const bool need = (it == 0) || (xmax > kRescaleThreshold);
+      if (__any_sync(0xffffffffu, need)) {
+        if (it > 0) {
+          mbar_wait(smem_u32(&bars->o_done), (it - 1) & 1);   // PV(it-1) must have landed in O
           tc_fence_after();
-          const float f = need ? ex2(m_used - cmax) : 1.0f;
-          if (need) m_used = cmax;
+          const float f = need ? ex2(-xmax) : 1.0f;
 #pragma unroll
           for (int c0 = 0; c0 < C::kDV; c0 += 16) {
             uint32_t o[16];
@@ -273,21 +290,26 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           tmem_st_wait();
         }
+        if (need) {
+          m_used += xmax;
+#pragma unroll
+          for (int c = 0; c < kBlockN; ++c) sreg[c] = __float_as_uint(__uint_as_float(sreg[c]) - xmax);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < kBlockN; c += 2) {
-        const float p0 = ex2(__uint_as_float(sreg[c]) - m_used);
-        const float p1 = ex2(__uint_as_float(sreg[c + 1]) - m_used);
-        preg[c >> 1] = pack_bf16(p0, p1);
-      }
+      for (int c = 0; c < kBlockN; c += 2)
+        preg[c >> 1] = pack_bf16(ex2(__uint_as_float(sreg[c])), ex2(__uint_as_float(sreg[c + 1])));
+      if (DBG && stamps) stamps[4] = clock64() + (long long)(preg[0] & 1u);
       if (it > 0) {   // PV(it-1) has finished reading the single P buffer
         mbar_wait(smem_u32(&bars->o_done), (it - 1) & 1);
         tc_fence_after();
       }
+      if (DBG && stamps) stamps[5] = clock64();
       tmem_st_x32(tlane + C::kColP, preg);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->p_full));
+      if (DBG && stamps) stamps[6] = clock64();
     }
 
     // epilogue: O[:, 0:D] / O[:, D]  ->  out[r, n, h*D : (h+1)*D]
@@ -365,12 +387,10 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   if ((rc = make_map(&tmQ, q, (uint64_t)R * N, (uint64_t)H * D, kBlockM)) != CVD_OK) return rc;
   if ((rc = make_map(&tmK, k, (uint64_t)R_kv * N, (uint64_t)H * D, kBlockN)) != CVD_OK) return rc;
   if ((rc = make_map(&tmV, vt, (uint64_t)R_kv * H * C::kDV, (uint64_t)N, C::kDV)) != CVD_OK) return rc;
-  auto kern = epi_attn_fwd_kernel<D, FEAT>;
-  static bool configured = false;
-  if (!configured) {
-    CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
-  }
+  constexpr bool kHasDebug = (D == 40 && FEAT == 32);   // the S-dump variant is built for the bench shape only
+  CVD_REQUIRE(dbg == nullptr || kHasDebug, "cvd_epi_attn_fwd_debug: only (head_dim=40, feat=32) has a debug build");
+  auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug> : epi_attn_fwd_kernel<D, FEAT, false>;
+  CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);

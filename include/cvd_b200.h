@@ -83,7 +83,8 @@ int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, const float* 
                      int n_partners, int feat, float F_mat_size, cvd_stream_t stream);
 
 /* Bring-up aid: as cvd_epi_attn_fwd, and additionally dumps the raw Q K^T accumulator of key
- * tile 0 of every CTA into dbg_s (fp32 [R*heads*ceil(N/128), 128, 64]). */
+ * tile 0 of every CTA into dbg_s (fp32 [grid, 128, 64], grid = R*heads*ceil(N/128)), followed by
+ * int64 [grid, 32, 8] clock64 stamps of thread 0 at the hand-off points of each key tile. */
 int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const float* rowp,
                            const int* partner, void* out, float* dbg_s, int R, int R_kv, int N,
                            int heads, int head_dim, int n_partners, int feat, float F_mat_size,
