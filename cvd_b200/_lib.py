@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcvd_b200.so")
+LIB_PATH = os.environ.get("CVD_B200_LIB", os.path.join(_HERE, "lib", "libcvd_b200.so"))   # override: kernel experiments only
 
 OK = 0
 DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2

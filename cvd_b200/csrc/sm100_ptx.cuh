@@ -31,31 +31,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots burnt) until the
-// phase completes or ~hint_ns elapse.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must end in a trap (CUDA error on the host), never in a hung GPU.
+// Bounded wait.  mbarrier.try_wait blocks in hardware for a system-dependent time and wakes on the
+// phase flip, so the loop body runs rarely; a protocol bug must end in a trap (CUDA error on the
+// host), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
   uint32_t tries = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
-    if ((++tries & 255u) == 0u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
-    }
+  while (!mbar_try_wait(bar, parity)) {
+    if (++tries > (1u << 22)) __trap();
   }
+}
+
+// One elected lane of a fully converged warp (elect.sync): the canonical guard for tcgen05.mma /
+// tcgen05.commit / TMA issue.  Unlike `if (lane == 0)` it lets ptxas predicate the uniform-datapath
+// instruction directly instead of wrapping every one in an election loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- proxy / tcgen05 fences -------------------------------------------------------------

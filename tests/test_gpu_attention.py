@@ -64,7 +64,7 @@ def test_qk_accumulator_dump(golden, dev):
     N = feat * feat
     q, k, v, vt, rowp, bias, partner = make_case(dev, R, feat, H, d, 5, golden)
     grid = R * H * (N // 128)
-    dbg_all = torch.zeros(grid * 128 * 64 + grid * 32 * 8 * 2, device=dev, dtype=torch.float32)   # S dump + int64 stamps
+    dbg_all = torch.zeros(grid * 128 * 64 + 2 * grid * 32 * 8 * 2, device=dev, dtype=torch.float32)   # S dump + int64 stamps
     ops.epi_attn_fwd(q, k, vt, rowp, partner, H, 256.0, dbg_s=dbg_all)
     dbg = dbg_all[:grid * 128 * 64]
     torch.cuda.synchronize()
