@@ -55,6 +55,19 @@ def load_peaks():
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+    committed ncu --set full capture of this round (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_epi_attn_d40_ncu_full.json")
+    try:
+        d = json.load(open(path))
+        rd = float(d["dram__bytes_read.sum"].split()[0]) * 1e6
+        wr = float(d["dram__bytes_write.sum"].split()[0]) * 1e6
+        return rd + wr
+    except Exception:
+        return None
+
+
 def golden_F():
     g = np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))
     return torch.from_numpy(g["F_mats"])          # [32,3,3]: rows 0-15 view A->B, 16-31 view B->A
@@ -323,7 +336,8 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "epi_attn_fwd_kernel<40,32> (R=64, N=M=1024, C=320)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": big_ms,
+                         "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes per launch (ncu, profiles/r01_epi_attn_d40_ncu_full.json)",
+                         "peak_source": peak_src, "ms_per_launch": big_ms,
                          "algorithmic_flops_per_launch": big_flops},
             "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                              "sample": f"oracle EpiSelfAttention.forward, 1 call per shape ({cb_flops / 1e9:.1f} GFLOP), best of 2"},

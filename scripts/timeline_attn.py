@@ -22,23 +22,22 @@ for _ in range(2):
     ops.epi_attn_fwd(q, k, vt, rowp, partner, H, 256.0, dbg_s=buf)
 torch.cuda.synchronize()
 allst = buf[grid * 128 * 64:].view(torch.int64).view(2, grid, 32, 8).cpu().numpy()
-st = allst[0][:, :32, :6]
-mm = allst[1][:, :30, :5]
-names = ["wait s_full", "tmem ld", "score+max", "exp+pack(+rescale)", "P st+arrive"]
-d_ = np.diff(st, axis=2)                       # [grid,16,6]
-gap = st[:, 1:, 0] - st[:, :-1, 5]             # loop overhead between iterations
-life = st[:, 31, 5] - st[:, 2, 0]
-for sel, label in ((slice(0, 296), "first wave"), (slice(1000, 3000), "steady CTAs")):
+st = allst[0][:, :16, :6]
+mm = allst[1][:, :15, :5]
+names = ["wait s_full", "half0 ld+score+exp", "half1 ld+score+exp", "wait pv_done", "P st+arrive"]
+d_ = np.diff(st, axis=2)
+gap = st[:, 1:, 0] - st[:, :-1, 5]
+life = st[:, 15, 5] - st[:, 1, 0]
+for sel, label in ((slice(0, 444), "first wave"), (slice(1000, 3000), "steady CTAs")):
     print(label)
     for i, nm in enumerate(names):
-        print(f"  {nm:22s} it0={d_[sel, 0, i].mean():8.0f}  t2..31 mean={d_[sel, 2:, i].mean():8.0f}  p90={np.percentile(d_[sel, 2:, i], 90):8.0f}")
+        print(f"  {nm:22s} t1..15 mean={d_[sel, 1:, i].mean():8.0f}  p90={np.percentile(d_[sel, 1:, i], 90):8.0f}")
     print(f"  loop gap               mean={gap[sel].mean():8.0f}")
-    print(f"  sub-tiles 2..31 span   mean={life[sel].mean():8.0f}  per-subtile={life[sel].mean() / 30:8.0f}")
-
+    print(f"  tiles 1..15 span       mean={life[sel].mean():8.0f}  per-tile={life[sel].mean() / 15:8.0f}")
 md = np.diff(mm, axis=2)
-mnames = ["wait v/p_full", "issue PV (2 MMA)", "commits", "issue QK(t+2) (wait k + 3 MMA + commits)"]
+mnames = ["wait s_free", "issue QK(j+1) (wait k + 3 MMA + 2 commits)", "wait v_full/p_full", "issue PV (4 MMA + commits)"]
 sel = slice(1000, 3000)
-print("MMA thread (steady CTAs)")
+print("MMA warp (steady CTAs)")
 for i, nm in enumerate(mnames):
-    print(f"  {nm:42s} t2..29 mean={md[sel, 2:, i].mean():8.0f}  p90={np.percentile(md[sel, 2:, i], 90):8.0f}")
-print(f"  per-subtile period                          mean={(mm[sel, 29, 0] - mm[sel, 2, 0]).mean() / 27:8.0f}")
+    print(f"  {nm:44s} j1..13 mean={md[sel, 1:14, i].mean():8.0f}  p90={np.percentile(md[sel, 1:14, i], 90):8.0f}")
+print(f"  per-tile period                              mean={(mm[sel, 14, 0] - mm[sel, 1, 0]).mean() / 13:8.0f}")
