@@ -205,6 +205,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     shard = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"

@@ -12,6 +12,7 @@ the package does not load it, the first op does -- and raises if it has not been
 """
 from . import _lib, geometry, ops  # noqa: F401
 from ._lib import CvdError  # noqa: F401
+from .graphs import GraphedModule  # noqa: F401
 from .epi_module import (EpiAttnProcessor, EpiEncoding, EpiModule, EpiSelfAttention, EpiTransformer3DModel,  # noqa: F401
                          EpiTransformerBlock, FeedForward, get_epi_module)
 from .motion_module import (AttnProcessor, PoseAdaptorAttnProcessor, PositionalEncoding, TemporalSelfAttention,  # noqa: F401

@@ -464,7 +464,11 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   constexpr bool kHasDebug = (D == 40 && FEAT == 32);   // the S-dump variant is built for the bench shape only
   CVD_REQUIRE(dbg == nullptr || kHasDebug, "cvd_epi_attn_fwd_debug: only (head_dim=40, feat=32) has a debug build");
   auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug> : epi_attn_fwd_kernel<D, FEAT, false>;
-  CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  static bool configured[2] = {false, false};   // one process per GPU: set the attribute once per kernel
+  if (!configured[dbg != nullptr]) {
+    CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured[dbg != nullptr] = true;
+  }
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);

@@ -15,7 +15,37 @@ __device__ __forceinline__ size_t token_of(int b, int f, int p, int F, int HW, i
 // GroupNorm statistics: one CTA per (b, f, group).  resnet.py:30-40 applies nn.GroupNorm
 // per frame, so a group is cpg channels x HW pixels of ONE frame (channel stride F*HW).
 // ---------------------------------------------------------------------------------------
-template <typename T>
+// 16-byte vector loads of the native dtype, widened to float
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  __device__ static void load(const __half* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  }
+};
+
+// Single pass, shifted by the group's first element so that sum((x-x0)^2) - n*mean(x-x0)^2 stays
+// well conditioned; 16-byte loads when HW allows.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restrict__ x, float* __restrict__ stats,
                                                               int C, int F, int HW, int groups, float eps) {
   const int g = blockIdx.x % groups;
@@ -25,34 +55,46 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const T* __restric
   const int n = cpg * HW;
   const T* base = x + (((size_t)b * C + (size_t)g * cpg) * F + f) * HW;
   const size_t cstride = (size_t)F * HW;
-  __shared__ float red[8];
-  __shared__ float bc;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += load_as_float(base, (size_t)(i / HW) * cstride + (i % HW));
+  const float x0 = load_as_float(base, 0);
+  float s = 0.f, q = 0.f;
+  if (VEC) {
+    constexpr int V = Vec16<T>::N;
+    const int per_c = HW / V;
+    for (int i = threadIdx.x; i < cpg * per_c; i += blockDim.x) {
+      float v[V];
+      Vec16<T>::load(base + (size_t)(i / per_c) * cstride + (size_t)(i % per_c) * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float d = v[k] - x0;
+        s += d;
+        q = fmaf(d, d, q);
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float d = load_as_float(base, (size_t)(i / HW) * cstride + (i % HW)) - x0;
+      s += d;
+      q = fmaf(d, d, q);
+    }
+  }
+  __shared__ float rs[8], rq[8];
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    bc = t / (float)n;
+  q = warp_sum(q);
+  if ((threadIdx.x & 31) == 0) {
+    rs[threadIdx.x >> 5] = s;
+    rq[threadIdx.x >> 5] = q;
   }
   __syncthreads();
-  const float mean = bc;
-  float v = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float d = load_as_float(base, (size_t)(i / HW) * cstride + (i % HW)) - mean;
-    v = fmaf(d, d, v);
-  }
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    stats[2 * (size_t)blockIdx.x] = mean;
-    stats[2 * (size_t)blockIdx.x + 1] = rsqrtf(t / (float)n + eps);
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      ts += rs[i];
+      tq += rq[i];
+    }
+    const float md = ts / (float)n;
+    const float var = fmaxf(tq / (float)n - md * md, 0.f);
+    stats[2 * (size_t)blockIdx.x] = x0 + md;
+    stats[2 * (size_t)blockIdx.x + 1] = rsqrtf(var + eps);
   }
 }
 
@@ -254,7 +296,11 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const uint4* __restrict_
 template <typename T>
 static int launch_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B,
                                    int C, int F, int HW, int groups, float eps, int layout, cudaStream_t st) {
-  groupnorm_stats_kernel<T><<<B * F * groups, 256, 0, st>>>((const T*)x, stats, C, F, HW, groups, eps);
+  const bool vec = (HW % Vec16<T>::N == 0) && (((uintptr_t)x & 15) == 0);
+  if (vec)
+    groupnorm_stats_kernel<T, true><<<B * F * groups, 256, 0, st>>>((const T*)x, stats, C, F, HW, groups, eps);
+  else
+    groupnorm_stats_kernel<T, false><<<B * F * groups, 256, 0, st>>>((const T*)x, stats, C, F, HW, groups, eps);
   CVD_LAUNCH_CHECK("groupnorm_stats_kernel");
   dim3 grid((HW + kTileP - 1) / kTileP, (C + kTileC - 1) / kTileC, B * F);
   video_to_tokens_kernel<T, 0><<<grid, 256, 0, st>>>((const T*)x, stats, gamma, beta, nullptr, (__nv_bfloat16*)y, C, F,

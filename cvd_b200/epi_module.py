@@ -214,9 +214,9 @@ class EpiAttnProcessor(nn.Module):
         w = attn._w
         q = F.linear(x, w.bf16("q", attn.to_q.weight))
         k = F.linear(x, w.bf16("k", attn.to_k.weight))
-        wv, bv = attn.padded_v_weights()
-        # V^T per head with a row of ones: [R, H*DV, N] = bias + Wv_pad @ x^T
-        vt = torch.baddbmm(bv, wv.unsqueeze(0).expand(R, -1, -1), x.transpose(1, 2)).view(R, H, ops.dv_rows(d), N)
+        # V^T per head: [R, H*DV, N] = Wv_pad @ x^T (zero rows on the padding), then row d of every head := 1
+        vt = torch.matmul(attn.padded_v_weights(), x.transpose(1, 2)).view(R, H, ops.dv_rows(d), N)
+        vt[:, :, d].fill_(1.0)
         k_src, vt_src = k, vt
         if self.shard is not None:
             # view sharding: partner rows live on other ranks -> one K / V^T all-gather per call;
@@ -280,17 +280,14 @@ class EpiSelfAttention(nn.Module):
         pass   # epi_module.py:379-384
 
     def padded_v_weights(self):
-        """to_v as the [H*DV, C] operand of the V^T GEMM (zero rows on the padding) and its
-        bias column [1, H*DV, 1] holding 1.0 on row ``d`` of every head."""
+        """to_v as the [H*DV, C] operand of the V^T GEMM: DV rows per head, zero rows on the padding."""
         def make(wv):
             H, C = self.heads, wv.shape[1]
             d = wv.shape[0] // H
             DV = ops.dv_rows(d)
             wp = torch.zeros(H, DV, C, device=wv.device, dtype=torch.bfloat16)
             wp[:, :d] = wv.detach().view(H, d, C).to(torch.bfloat16)
-            b = torch.zeros(H, DV, device=wv.device, dtype=torch.bfloat16)
-            b[:, d] = 1.0
-            return wp.view(H * DV, C).contiguous(), b.view(1, H * DV, 1).contiguous()
+            return wp.view(H * DV, C).contiguous()
         return self._w.get("v_pad", self.to_v.weight, make)
 
     def attend(self, hidden_states, F_mats=None, H_mats=None, **kw):
