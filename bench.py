@@ -41,6 +41,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
+EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -183,7 +184,7 @@ def workload_config(n_gpus):
     return {"workload": "CVD two-video inference (BASELINE config 2): 40 epi-attention calls of one UNet forward, "
                         "R=64 rows per GPU (2 views x 2 cfg x 16 frames), (N,C) = (1024,320),(256,640),(64,1280),(16,1280) x10, 8 heads",
             "rows_per_gpu": R_PER_GPU, "views_total": 2 * n_gpus, "flops_per_step": step_flops(R_PER_GPU * n_gpus),
-            "parallelism": "1 GPU" if n_gpus == 1 else f"views sharded over {n_gpus} GPUs, K/V^T all-gather per call (NCCL)",
+            "parallelism": "1 GPU" if n_gpus == 1 else f"views sharded over {n_gpus} GPUs, partner K/V^T rows pulled per call ({EXCHANGE})",
             "l2_policy": "inputs larger than L2: distinct q/k/v^T buffers per call (1.9 GB per step)"}
 
 
@@ -203,11 +204,13 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    shard = None
+    shard = peer = None
     if world > 1:
         os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
+        if args.exchange == "peer":
+            peer = sharding.PeerExchange(shard)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _lib.load()
     R = R_PER_GPU
@@ -231,28 +234,49 @@ def run_ours(args):
         per_call = []
         for _ in range(CALLS_PER_SHAPE):
             q = torch.randn(R, N, C, device=dev, generator=gen).to(torch.bfloat16)
-            k = torch.randn(R, N, C, device=dev, generator=gen).to(torch.bfloat16)
-            vt = torch.zeros(R, HEADS, ops.dv_rows(d), N, device=dev, dtype=torch.bfloat16)
+            if peer is None:
+                k = torch.empty(R, N, C, device=dev, dtype=torch.bfloat16)
+                vt = torch.empty(R, HEADS, ops.dv_rows(d), N, device=dev, dtype=torch.bfloat16)
+                xk = xv = None
+            else:   # K / V^T resident in symmetric memory: the peers pull their partner rows from here
+                k, pk, hk = peer.alloc((R, N, C), torch.bfloat16, dev)
+                vt, pv, hv = peer.alloc((R, HEADS, ops.dv_rows(d), N), torch.bfloat16, dev)
+                xk, xv = (pk, hk), (pv, hv)
+            k.copy_(torch.randn(R, N, C, device=dev, generator=gen))
+            vt.zero_()
             vt[:, :, :d] = torch.randn(R, HEADS, d, N, device=dev, generator=gen).to(torch.bfloat16)
             vt[:, :, d] = 1.0
-            per_call.append((q, k, vt))
+            per_call.append((q, k, vt, xk, xv))
         bufs.append(per_call)
+    # landing buffers of the pulled partner rows (one pair per shape, reused by its 10 calls)
+    land = [None if peer is None else (torch.empty_like(pc[0][1]), torch.empty_like(pc[0][2])) for pc in bufs]
+    ident = None if peer is None else peer.identity_index(R, dev)
     theta = torch.tensor([0.5], device=dev)
     big_events = []
 
     def value_step(record):
-        for (feat, C), per_call in zip(SHAPES, bufs):
-            for q, k, vt in per_call:
+        for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
+            for q, k, vt, xk, xv in per_call:
                 rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
-                ks, vs = (k, vt) if shard is None else (shard.gather_rows(k), shard.gather_rows(vt))
+                idx = partner
+                if shard is None:
+                    ks, vs = k, vt
+                elif peer is None:            # baseline: NCCL all-gather of every rank's K and V^T
+                    ks, vs = shard.gather_rows(k), shard.gather_rows(vt)
+                else:                         # one cross-rank barrier, then pull only the partner rows over NVLink
+                    # (pulling in row chunks on a side stream under the attention of the previous chunk was
+                    # measured slower: the pull kernel and the smaller attention grids compete for SMs)
+                    ks = peer.pull(xk[0], xk[1], partner, ld[0], rows_per_src=R)
+                    vs = ops.peer_gather_rows(xv[0], partner, ld[1], rows_per_src=R)
+                    idx = ident
                 if record and feat == SHAPES[0][0]:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
-                    ops.epi_attn_fwd(q, ks, vs, rowp, partner, HEADS, F_MAT_SIZE)
+                    ops.epi_attn_fwd(q, ks, vs, rowp, idx, HEADS, F_MAT_SIZE)
                     e1.record()
-                    big_events.append((e0, e1))
+                    big_events.append((e0, e1, 1))
                 else:
-                    ops.epi_attn_fwd(q, ks, vs, rowp, partner, HEADS, F_MAT_SIZE)
+                    ops.epi_attn_fwd(q, ks, vs, rowp, idx, HEADS, F_MAT_SIZE)
 
     def barrier():
         if world > 1:
@@ -274,7 +298,7 @@ def run_ours(args):
     launches = ops.LAUNCHES - launches0
     ms_value = t0.elapsed_time(t1) / args.steps
     clk = clocks.stop()
-    big_ms = float(np.mean([a.elapsed_time(b) for a, b in big_events]))
+    big_ms = float(np.mean([a.elapsed_time(b) * n for a, b, n in big_events]))   # per full-R launch equivalent
 
     # ---------------- e2e: layer API with host buffers ----------------
     layers, hosts = [], []
@@ -286,6 +310,7 @@ def run_ours(args):
         attn.load_state_dict(gi.attn_state_dict(C, 10 + feat), strict=False)
         attn = attn.to(dev).eval()
         attn.processor.shard = shard
+        attn.processor.peer = peer
         layers.append(attn)
         x_host = torch.randn(R, feat * feat, C, generator=torch.Generator().manual_seed(feat)).pin_memory()
         y_host = torch.empty_like(x_host).pin_memory()
@@ -294,13 +319,32 @@ def run_ours(args):
     h2d = sum(CALLS_PER_SHAPE * x.numel() * 4 for x, _ in hosts)
     d2h = h2d
 
+    # H2D, compute and D2H run on three streams with a 3-deep ring of device buffers per shape, so the
+    # PCIe transfers of neighbouring calls overlap the kernels (all of it inside the timed region).
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ring = 3
+    dev_in = [[torch.empty_like(x, device=dev) for _ in range(ring)] for x, _ in hosts]
+    ev_in = [[torch.cuda.Event() for _ in range(ring)] for _ in hosts]
+    ev_done = [[torch.cuda.Event() for _ in range(ring)] for _ in hosts]
+    main = torch.cuda.current_stream()
+
     def e2e_step():
         with torch.no_grad():
-            for attn, (x_host, y_host) in zip(layers, hosts):
-                for _ in range(CALLS_PER_SHAPE):
-                    x = x_host.to(dev, non_blocking=True)
-                    y, _aux = attn(x, F_mats=F_rows if kv_index is None else [F_rows, kv_index])
-                    y_host.copy_(y, non_blocking=True)
+            for li, (attn, (x_host, y_host)) in enumerate(zip(layers, hosts)):
+                for c in range(CALLS_PER_SHAPE):
+                    b = c % ring
+                    with torch.cuda.stream(s_in):
+                        s_in.wait_event(ev_done[li][b])          # the previous user of this slot has consumed it
+                        dev_in[li][b].copy_(x_host, non_blocking=True)
+                        ev_in[li][b].record(s_in)
+                    main.wait_event(ev_in[li][b])
+                    y, _aux = attn(dev_in[li][b], F_mats=F_rows if kv_index is None else [F_rows, kv_index])
+                    ev_done[li][b].record(main)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ev_done[li][b])
+                        y_host.copy_(y, non_blocking=True)
+                        y.record_stream(s_out)
+        main.wait_stream(s_out)
 
     for _ in range(3):
         e2e_step()
@@ -332,7 +376,7 @@ def run_ours(args):
             "config": workload_config(world),
             "e2e": {"value": flops / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "cvd_b200.EpiSelfAttention.forward (fp32 host tensors, pinned)"},
+                    "api": "cvd_b200.EpiSelfAttention.forward (fp32 pinned host tensors; H2D / compute / D2H on 3 streams)"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "epi_attn_fwd_kernel<40,32> (R=64, N=M=1024, C=320)",
@@ -354,7 +398,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
+                    help="N>1: pull partner rows over NVLink peer memory (default) or NCCL all-gather (baseline)")
     args = ap.parse_args()
+    global EXCHANGE
+    if args.exchange == "allgather":
+        EXCHANGE = "NCCL all-gather"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -159,7 +159,8 @@ class EpiAttnProcessor(nn.Module):
         self.hidden_size = hidden_size
         self.scale = scale
         self._idx = {}
-        self.shard = None   # cvd_b200.sharding.ViewShard: rows are sharded by view, K/V all-gathered per call
+        self.shard = None   # cvd_b200.sharding.ViewShard: rows are sharded by view (baseline: K/V^T all-gather per call)
+        self.peer = None    # cvd_b200.sharding.PeerExchange: pull the partner rows over NVLink instead (product path)
 
     def partner_index(self, R, kv_index, device):
         """int32 device index: row r reads K/V of row partner[p*R + r]
@@ -213,12 +214,19 @@ class EpiAttnProcessor(nn.Module):
             partner = self.partner_index(R, kv_index, x.device)
         w = attn._w
         q = F.linear(x, w.bf16("q", attn.to_q.weight))
-        k = F.linear(x, w.bf16("k", attn.to_k.weight))
+        x_kv = x
+        if self.peer is not None:
+            # view sharding, product path: pull the partner rows of the (LayerNorm-ed) hidden states out of the
+            # peers' HBM -- half the bytes of K and V^T -- and project K / V^T of exactly those rows here
+            x_kv = self.peer.exchange(x, partner)
+            partner = self.peer.identity_index(x_kv.shape[0], x.device)
+        Rk = x_kv.shape[0]
+        k = F.linear(x_kv, w.bf16("k", attn.to_k.weight))
         # V^T per head: [R, H*DV, N] = Wv_pad @ x^T (zero rows on the padding), then row d of every head := 1
-        vt = torch.matmul(attn.padded_v_weights(), x.transpose(1, 2)).view(R, H, ops.dv_rows(d), N)
+        vt = torch.matmul(attn.padded_v_weights(), x_kv.transpose(1, 2)).view(Rk, H, ops.dv_rows(d), N)
         vt[:, :, d].fill_(1.0)
         k_src, vt_src = k, vt
-        if self.shard is not None:
+        if self.shard is not None and self.peer is None:
             # view sharding: partner rows live on other ranks -> one K / V^T all-gather per call;
             # `partner` / kv_index then address rows of the gathered (global) buffers
             k_src, vt_src = self.shard.gather_rows(k), self.shard.gather_rows(vt)

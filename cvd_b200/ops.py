@@ -186,3 +186,16 @@ def scale_add(a, b, scale):
               out.data_ptr(), a.numel(), _stream())
     _count()
     return out
+
+
+def peer_gather_rows(src_ptrs, partner, dst, rows_per_src):
+    """dst[r] = rows of the peers' buffers (device pointers ``src_ptrs``, one per rank) selected by the
+    GLOBAL row numbers ``partner`` (int32 device tensor).  ``dst``: contiguous [rows, ...] CUDA tensor."""
+    import ctypes
+    rows = partner.shape[0]
+    row_bytes = dst.numel() // rows * dst.element_size()
+    arr = (ctypes.c_void_p * len(src_ptrs))(*[int(p) for p in src_ptrs])
+    _lib.call("cvd_peer_gather_rows", ctypes.cast(arr, ctypes.c_void_p), len(src_ptrs), _check(partner, torch.int32, "partner"),
+              _check(dst, None, "dst"), rows, rows_per_src, row_bytes, _stream())
+    _count()
+    return dst

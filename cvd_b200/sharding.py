@@ -3,9 +3,17 @@
 Everything in the UNet is per video or per frame except the epi attention, where row r reads
 the K/V of a *different view, same frame* (``attention_processor.py:573-583``;
 ``pipeline_animation_epi_advanced.py:621-633``).  So (view, cfg) units shard across ranks with
-one exchange per epi-attention call: every rank projects K and V^T for its own rows, the
-shards are all-gathered (NCCL over NVLink; row order = rank order), and the fused kernel
-indexes the gathered buffer with GLOBAL partner rows.  No other collective is on the path.
+one exchange per epi-attention call and no other collective on the path.
+
+Two exchange mechanisms:
+
+* ``PeerExchange`` (product path): the LayerNorm-ed hidden states (layer API) or K / V^T (kernel
+  benchmark) live in symmetric memory; after a device-side cross-rank barrier every rank PULLS
+  exactly the rows its queries attend to out of its peers' HBM with ``cvd_peer_gather_rows``
+  (our kernel, 16-byte loads over NVLink).  R_local rows cross the links per call whatever the
+  world size, and there is no collective launch.
+* ``ViewShard.gather_rows`` (baseline, and the CPU/gloo test path): NCCL all-gather of every rank's
+  rows; the attention kernel then indexes the gathered buffer with GLOBAL partner rows.
 
 The reference has no multi-GPU inference; this layout is new.
 """
@@ -52,3 +60,61 @@ class ViewShard:
         parts = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(parts, t, group=self.group)
         return torch.cat(parts, dim=0)
+
+
+class PeerExchange:
+    """Symmetric-memory workspaces (two slots per shape, used alternately) + peer row pull.
+
+    Protocol per call: write the local rows into the current slot (stream-ordered), ``barrier``
+    (device-side, all ranks), pull the partner rows from the peers' copies of that slot.  With two
+    slots one barrier per call is enough: a slot is rewritten two calls later, after a barrier that
+    every rank only passes once its earlier pull (stream-ordered before it) has been issued."""
+
+    def __init__(self, shard: ViewShard):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.shard = shard
+        self.group = shard.group if shard.group is not None else dist.group.WORLD
+        self._slots = {}
+        self._arange = {}
+
+    def alloc(self, shape, dtype, device):
+        """One symmetric buffer (a collective call: every rank must allocate in the same order).
+        Returns (local tensor, peer base pointers in rank order, handle)."""
+        t = self.symm_mem.empty(*shape, dtype=dtype, device=device)
+        hdl = self.symm_mem.rendezvous(t, self.group)
+        ptrs = [hdl.get_buffer(r, tuple(shape), dtype).data_ptr() for r in range(self.shard.world)]
+        return t, ptrs, hdl
+
+    def slot(self, shape, dtype, device):
+        key = (tuple(shape), dtype)
+        e = self._slots.get(key)
+        if e is None:
+            e = {"bufs": [self.alloc(shape, dtype, device) for _ in range(2)], "next": 0}
+            self._slots[key] = e
+        b = e["bufs"][e["next"]]
+        e["next"] ^= 1
+        return b
+
+    def pull(self, ptrs, hdl, partner, out, rows_per_src):
+        """out[r] = peers' row partner[r] (GLOBAL numbering) of an already written symmetric buffer,
+        after a cross-rank barrier."""
+        from . import ops
+        hdl.barrier()
+        return ops.peer_gather_rows(ptrs, partner, out, rows_per_src=rows_per_src)
+
+    def exchange(self, x, partner):
+        """x: local rows [R_loc, ...] (any contiguous CUDA tensor).  Returns the partner rows
+        [len(partner), ...] pulled from the peers (partner: int32 device tensor of GLOBAL rows)."""
+        from . import ops
+        local, ptrs, hdl = self.slot(x.shape, x.dtype, x.device)
+        local.copy_(x)
+        hdl.barrier()
+        out = torch.empty((partner.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+        return ops.peer_gather_rows(ptrs, partner, out, rows_per_src=x.shape[0])
+
+    def identity_index(self, n, device):
+        key = (n, device)
+        if key not in self._arange:
+            self._arange[key] = torch.arange(n, device=device, dtype=torch.int32)
+        return self._arange[key]

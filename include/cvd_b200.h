@@ -141,6 +141,15 @@ int cvd_add_pose_tokens_fwd(const void* x_tok, const void* pose, int pose_dtype,
 int cvd_scale_add_fwd(const void* a, const void* b, float scale, void* out, long long n,
                       cvd_stream_t stream);
 
+/* ---- multi-GPU view sharding (new; the reference has no multi-GPU inference): pull the rows this
+ *      rank's queries attend to out of the peers' memory over NVLink.
+ *        dst[r] = src_bases[partner[r] / rows_per_src][partner[r] % rows_per_src],  r < rows
+ *      src_bases: HOST array of n_src (<= 8) device pointers (peer-mapped, e.g. symmetric memory);
+ *      partner: device int32 [rows] of GLOBAL row numbers; rows are row_bytes (multiple of 16) long.
+ *      The caller orders it after the peers' writes (cross-rank barrier). */
+int cvd_peer_gather_rows(const void* const* src_bases, int n_src, const int* partner, void* dst,
+                         int rows, int rows_per_src, long long row_bytes, cvd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
