@@ -35,6 +35,7 @@ SIGNATURES = {
     "cvd_add_pose_tokens_fwd": [_P, _P, _I, _P, _I, _I, _I, _I, _P],
     "cvd_scale_add_fwd": [_P, _P, _F, _P, _LL, _P],
     "cvd_peer_gather_rows": [_P, _I, _P, _P, _I, _I, _LL, _P],
+    "cvd_pairwise_fundamental": [_P, _P, _P, _P, _I, _P],
 }
 
 _lib = None

@@ -1,0 +1,63 @@
+// Pose -> fundamental matrices on the device: the per-UNet-call loop of the V-view sampler
+// (animatediff/pipelines/pipeline_animation_epi_advanced.py:636-647 calling
+// animatediff/data/dataset_validation.py:28-64) as one kernel launch.  One thread per row:
+//   s2t = inv(c2w[tgt]) c2w[src];  E = R [(-R^T t)]x;  F = K_tgt^-T E K_src^-1      (fp64, like numpy)
+#include "common.cuh"
+
+namespace cvd {
+
+__device__ void inv3(const double* m, double* o) {
+  const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+  const double A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const double det = a * A + b * B + c * C;
+  const double r = 1.0 / det;
+  o[0] = A * r; o[1] = -(b * i - c * h) * r; o[2] = (b * f - c * e) * r;
+  o[3] = B * r; o[4] = (a * i - c * g) * r;  o[5] = -(a * f - c * d) * r;
+  o[6] = C * r; o[7] = -(a * h - b * g) * r; o[8] = (a * e - b * d) * r;
+}
+__device__ void mul3(const double* a, const double* b, double* o) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) o[r * 3 + c] = a[r * 3] * b[c] + a[r * 3 + 1] * b[3 + c] + a[r * 3 + 2] * b[6 + c];
+}
+
+__global__ void pairwise_fundamental_kernel(const double* __restrict__ c2w, const double* __restrict__ K,
+                                            const int* __restrict__ partner, float* __restrict__ F, int rows) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= rows) return;
+  const int t = partner[s];
+  const double* Ms = c2w + (size_t)s * 16;
+  const double* Mt = c2w + (size_t)t * 16;
+  // rigid inverse of the target pose: inv([R|p]) = [R^T | -R^T p]   (np.linalg.inv of a rigid 4x4)
+  double Rt[9], Rs[9], R[9], pt[3], ps[3], tr[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) { Rt[r * 3 + c] = Mt[c * 4 + r]; Rs[r * 3 + c] = Ms[r * 4 + c]; }
+    pt[r] = Mt[r * 4 + 3];
+    ps[r] = Ms[r * 4 + 3];
+  }
+  mul3(Rt, Rs, R);                                   // rotation of s2t
+  for (int r = 0; r < 3; ++r)                        // translation of s2t = R_t^T (p_s - p_t)
+    tr[r] = Rt[r * 3] * (ps[0] - pt[0]) + Rt[r * 3 + 1] * (ps[1] - pt[1]) + Rt[r * 3 + 2] * (ps[2] - pt[2]);
+  double te[3];                                      // t_ess = -R^T t
+  for (int r = 0; r < 3; ++r) te[r] = -(R[r] * tr[0] + R[3 + r] * tr[1] + R[6 + r] * tr[2]);
+  const double X[9] = {0.0, -te[2], te[1], te[2], 0.0, -te[0], -te[1], te[0], 0.0};
+  double E[9], K1i[9], K2i[9], K2iT[9], T1[9], Fm[9];
+  mul3(R, X, E);
+  inv3(K + (size_t)s * 9, K1i);
+  inv3(K + (size_t)t * 9, K2i);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) K2iT[r * 3 + c] = K2i[c * 3 + r];
+  mul3(K2iT, E, T1);
+  mul3(T1, K1i, Fm);
+  for (int i = 0; i < 9; ++i) F[(size_t)s * 9 + i] = (float)Fm[i];
+}
+
+}  // namespace cvd
+
+extern "C" int cvd_pairwise_fundamental(const double* c2w, const double* K, const int* partner, float* F_mats, int rows,
+                                        cvd_stream_t stream) {
+  CVD_REQUIRE(c2w && K && partner && F_mats, "cvd_pairwise_fundamental: null pointer");
+  CVD_REQUIRE(rows > 0, "cvd_pairwise_fundamental: rows=%d", rows);
+  cvd::pairwise_fundamental_kernel<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c2w, K, partner, F_mats, rows);
+  CVD_LAUNCH_CHECK("pairwise_fundamental_kernel");
+  return CVD_OK;
+}

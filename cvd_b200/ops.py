@@ -199,3 +199,14 @@ def peer_gather_rows(src_ptrs, partner, dst, rows_per_src):
               _check(dst, None, "dst"), rows, rows_per_src, row_bytes, _stream())
     _count()
     return dst
+
+
+def pairwise_fundamental(c2w, K, partner):
+    """Device version of the sampler's per-call F recompute: c2w fp64 [rows,4,4], K fp64 [rows,3,3],
+    partner int32 [rows] (target row of every source row) -> F_mats fp32 [rows,3,3]."""
+    rows = c2w.shape[0]
+    F_mats = torch.empty(rows, 3, 3, device=c2w.device, dtype=torch.float32)
+    _lib.call("cvd_pairwise_fundamental", _check(c2w, torch.float64, "c2w"), _check(K, torch.float64, "K"),
+              _check(partner, torch.int32, "partner"), F_mats.data_ptr(), rows, _stream())
+    _count()
+    return F_mats

@@ -141,6 +141,14 @@ int cvd_add_pose_tokens_fwd(const void* x_tok, const void* pose, int pose_dtype,
 int cvd_scale_add_fwd(const void* a, const void* b, float scale, void* out, long long n,
                       cvd_stream_t stream);
 
+/* ---- a11 on the device: per-row fundamental matrices of a view pairing, replacing the Python loop the
+ *      V-view sampler runs on the CPU before every UNet call
+ *      (pipelines/pipeline_animation_epi_advanced.py:636-647 -> data/dataset_validation.py:28-64):
+ *        F[s] = K[t]^-T E(inv(c2w[t]) c2w[s]) K[s]^-1,  t = partner[s]
+ *      c2w fp64 [rows,4,4] (rigid poses), K fp64 [rows,3,3], partner int32 [rows], F_mats fp32 [rows,3,3]. */
+int cvd_pairwise_fundamental(const double* c2w, const double* K, const int* partner, float* F_mats,
+                             int rows, cvd_stream_t stream);
+
 /* ---- multi-GPU view sharding (new; the reference has no multi-GPU inference): pull the rows this
  *      rank's queries attend to out of the peers' memory over NVLink.
  *        dst[r] = src_bases[partner[r] / rows_per_src][partner[r] % rows_per_src],  r < rows

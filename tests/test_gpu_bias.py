@@ -63,3 +63,26 @@ def test_bias_vs_oracle_random_F(dev):
         b, _ = dense(Fm, 32, 256, dev, theta)
         ref = O.epi_bias(Fm, 32, 256, theta=theta)
         np.testing.assert_allclose(b.numpy(), ref.numpy(), atol=5e-3, rtol=2e-4)
+
+
+def test_pairwise_fundamental_on_device(golden, dev):
+    """cvd_pairwise_fundamental == the reference's CPU loop (fixture F_mats of the shipped pose pair) and
+    == the oracle on a random 4-view pairing."""
+    from cvd_b200 import ops
+    from oracle import epi_oracle as O
+    g = golden["geometry"]
+    c2w = torch.from_numpy(g["c2w"][0].astype(np.float64)).to(dev).contiguous()
+    K = torch.from_numpy(g["K_mats"].astype(np.float64)).to(dev).contiguous()
+    partner = torch.cat([torch.arange(16, 32), torch.arange(0, 16)]).to(torch.int32).to(dev)
+    Fm = ops.pairwise_fundamental(c2w, K, partner).cpu()
+    np.testing.assert_allclose(Fm.numpy(), g["F_mats"], rtol=2e-4, atol=1e-9)
+    rng = np.random.RandomState(3)
+    from scipy.spatial.transform import Rotation
+    c = np.tile(np.eye(4), (64, 1, 1))
+    c[:, :3, :3] = Rotation.from_rotvec(rng.randn(64, 3) * 0.2).as_matrix()
+    c[:, :3, 3] = rng.randn(64, 3)
+    Km = np.tile(np.array([[223.578, 0, 128], [0, 223.578, 128], [0, 0, 1.0]]), (64, 1, 1))
+    pairing = [2, 3, 0, 1]
+    idx = np.concatenate([np.arange(16) + p * 16 for p in pairing]).astype(np.int32)
+    Fd = ops.pairwise_fundamental(torch.from_numpy(c).to(dev), torch.from_numpy(Km).to(dev), torch.from_numpy(idx).to(dev)).cpu()
+    np.testing.assert_allclose(Fd.numpy(), O.pairwise_F_mats(c, Km, pairing).numpy(), rtol=1e-5, atol=1e-9)

@@ -114,3 +114,21 @@ def test_cpu_tensor_is_refused():
     from cvd_b200 import CvdError, ops
     with pytest.raises(CvdError):
         ops.geglu(torch.zeros(4, 16, dtype=torch.bfloat16))
+
+
+def test_peer_gather_rows_single_gpu(dev):
+    """cvd_peer_gather_rows with two 'ranks' that are two local buffers: dst[r] = src[g // rows][g % rows]."""
+    from cvd_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(32, 16, 40, generator=g).to(dev).to(torch.bfloat16)
+    b = torch.randn(32, 16, 40, generator=g).to(dev).to(torch.bfloat16)
+    partner = torch.randperm(64, generator=g)[:48].to(torch.int32).to(dev)
+    dst = torch.empty(48, 16, 40, device=dev, dtype=torch.bfloat16)
+    ops.peer_gather_rows([a.data_ptr(), b.data_ptr()], partner, dst, rows_per_src=32)
+    ref = torch.cat([a, b])[partner.long()]
+    assert torch.equal(dst, ref)
+    big = torch.randn(8, 1024, 320, generator=g).to(dev).to(torch.bfloat16)       # long rows, several chunks per row
+    idx = torch.tensor([7, 0, 3, 3, 5], dtype=torch.int32, device=dev)
+    out = torch.empty(5, 1024, 320, device=dev, dtype=torch.bfloat16)
+    ops.peer_gather_rows([big.data_ptr()], idx, out, rows_per_src=8)
+    assert torch.equal(out, big[idx.long()])
