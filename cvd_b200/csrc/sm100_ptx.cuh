@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, int x, int y, int z, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"((uint64_t)m), "r"(x), "r"(y), "r"(z), "r"(bar)
+      : "memory");
+}
+
 // ---- TMEM allocation (one full warp) ----------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
