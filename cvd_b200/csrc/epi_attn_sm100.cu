@@ -30,11 +30,14 @@
 #include "sm100_ptx.cuh"
 
 namespace cvd {
+// csrc/epi_attn_small.cu: warp-level kernel for the N <= 64 grids; -1000 = not a small-grid configuration
+int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
+                            int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st);
 namespace sm100 {
 
 using namespace ptx;
 
-constexpr int kBlockM = 128;   // queries per work item (= TMEM lanes)
+constexpr int kBlockM = 128;   // queries per CTA (= TMEM lanes)
 constexpr int kTileN = 64;     // keys per TMA tile / MMA round
 constexpr int kHalfN = 32;     // scores a softmax thread holds in registers at a time
 constexpr int kThreads = 192;
@@ -46,82 +49,73 @@ struct Cfg {
   static_assert(D % 8 == 0 && (D % 16 == 0 || D % 16 == 8), "head_dim must be a multiple of 8");
   static constexpr int kN = FEAT * FEAT;
   static constexpr int kTiles = (kN + kTileN - 1) / kTileN;      // per partner
-  static constexpr int kQTiles = (kN + kBlockM - 1) / kBlockM;
   static constexpr int kKBlocks = (D + 63) / 64;          // 128-byte swizzle atoms along the head dim
   static constexpr int kKSteps = (D + 15) / 16;           // UMMA K steps of Q K^T
   static constexpr int kDV = (D / 16 + 1) * 16;           // rows of a V^T tile: d values, a row of ones, zero pad
   static constexpr int kQBytes = kKBlocks * kBlockM * 128;
   static constexpr int kKBytes = kKBlocks * kTileN * 128;
   static constexpr int kVBytes = kDV * 128;
-  // TMEM columns: S0 [0,64) | S1 [64,128) | O [128,128+DV) | P0 (32) [| P1 (32)]
-  //   d=40 : 256 columns, two P buffers, 2 CTAs per SM
-  //   d=80 : 256 columns, one  P buffer, 2 CTAs per SM
-  //   d=160: 512 columns, two P buffers, 1 CTA per SM
-  static constexpr int kColS = 0, kColO = 2 * kTileN;
-  static constexpr int kColP = ((kColO + kDV + 31) / 32) * 32;
-  static constexpr int kTmemCols = (kColP + 32 <= 256) ? 256 : 512;
-  static constexpr int kPBufs = (kColP + 64 <= kTmemCols) ? 2 : 1;
-  static constexpr int kCtasPerSM = kTmemCols == 256 ? 2 : 1;
-  static_assert(kColP + 32 * kPBufs <= kTmemCols, "TMEM budget");
-  // shared-memory rings
-  static constexpr int kQBufs = D == 80 ? 1 : 2;
-  static constexpr int kKStages = D <= 40 ? 4 : 3;
-  static constexpr int kVStages = D <= 40 ? 4 : 2;
-  static constexpr int kSmemData = kQBufs * kQBytes + kKStages * kKBytes + kVStages * kVBytes;
-  static constexpr int kSmemBytes = kSmemData + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(kSmemBytes * kCtasPerSM <= 227 * 1024, "shared memory budget");
+  // TMEM: S [0,64) | O [64,64+DV) in the main allocation.  P (32 columns of packed bf16):
+  //   d=40 : second 32-column allocation (128 + 32 columns per CTA -> 3 CTAs per SM)
+  //   d=80 : behind O inside a 256-column allocation
+  //   d=160: aliased onto S (then Q K^T of tile j+1 has to follow P_j V_j)
+  static constexpr int kColS = 0, kColO = kTileN;
+  static constexpr bool kAliasP = (kColO + kDV + kTileN / 2) > 256;
+  static constexpr bool kSplitP = !kAliasP && (kColO + kDV) <= 128;
+  static constexpr int kTmemCols = kSplitP ? 128 : 256;
+  static constexpr int kColP = kAliasP ? kColS : (kSplitP ? 0 : kColO + kDV);   // kSplitP: relative to the 2nd allocation
+  static_assert(kColO + kDV <= 256, "TMEM budget");
+  // K/V ring depth (never deeper than the tile count)
+  static constexpr int kWant = D <= 40 ? 3 : (D <= 80 ? 2 : (kTiles > 1 ? 2 : 1));
+  static constexpr int kKStages = kWant < kTiles ? kWant : kTiles;
+  static constexpr int kVStages = kKStages;
+  static constexpr int kSmemData = kQBytes + kKStages * kKBytes + kVStages * kVBytes;
+  // d=40 must NOT fit a 4th CTA (4 x 128 TMEM columns would starve the 32-column allocations)
+  static constexpr int kSmemBytes = (kSplitP && kSmemData < 58 * 1024 ? 58 * 1024 : kSmemData) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kMinBlocks = kSplitP ? 3 : (kSmemBytes <= 110 * 1024 ? 2 : 1);
 };
 
 struct Barriers {
-  uint64_t q_full[2], q_empty[2], s_full[2], s_free[2], p_full[2], p_free[2], o_done;
+  uint64_t q_full, s_full, s_free, p_full, pv_done, o_done;
   uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-  uint32_t tmem_base;
+  uint32_t tmem_base, tmem_p;
 };
 
-// Persistent kernel: CTA c works on items c, c + grid, ... (item = (row r, head h, 128-query tile)).
-// The key tiles of all its items form ONE stream g = 0, 1, ...; every ring (K/V stages, the two S
-// buffers, the P buffers, the Q buffers) is indexed by stream position, so the pipeline never
-// drains at an item boundary: Q K^T runs two tiles ahead of the softmax, and the O read-out of
-// item i happens inside the first tile of item i+1 (after its scores are in registers, before its
-// P is published).
 template <int D, int FEAT, bool DBG>
-__global__ void __launch_bounds__(kThreads, Cfg<D, FEAT>::kCtasPerSM)
+__global__ void __launch_bounds__(kThreads, Cfg<D, FEAT>::kMinBlocks)
 epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
                     const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R, int H, int n_partners,
                     float step, float* __restrict__ dbg) {
   using C = Cfg<D, FEAT>;
   constexpr int N = C::kN;
-  constexpr int kQTiles = C::kQTiles;
+  constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   constexpr int kRowsPerTile = (kTileN + FEAT - 1) / FEAT;   // key-grid rows touched by one key tile
   constexpr uint32_t kIdescQK = umma_idesc_bf16(kBlockM, kTileN);
   constexpr uint32_t kIdescPV = umma_idesc_bf16(kBlockM, C::kDV);
-  constexpr int QB = C::kQBufs, KS = C::kKStages, VS = C::kVStages, PB = C::kPBufs;
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + QB * C::kQBytes;
-  const uint32_t sV = sK + KS * C::kKBytes;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_raw + (sV + VS * C::kVBytes - smem_u32(smem_raw)));
+  const uint32_t sK = sQ + C::kQBytes;
+  const uint32_t sV = sK + C::kKStages * C::kKBytes;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_raw + (sV + C::kVStages * C::kVBytes - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = n_partners * C::kTiles;           // key tiles per item
-  const int n_items = R * H * kQTiles;
-  (void)lane;
+  const int qt = blockIdx.x % kQTiles;
+  const int h = (blockIdx.x / kQTiles) % H;
+  const int r = blockIdx.x / (kQTiles * H);
+  const int total = n_partners * C::kTiles;
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&bars->q_full[i]), 1);
-      mbar_init(smem_u32(&bars->q_empty[i]), 1);
-      mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->s_free[i]), 128);
-      mbar_init(smem_u32(&bars->p_full[i]), 128);
-      mbar_init(smem_u32(&bars->p_free[i]), 1);
-    }
+    mbar_init(smem_u32(&bars->q_full), 1);
+    mbar_init(smem_u32(&bars->s_full), 1);
+    mbar_init(smem_u32(&bars->s_free), 128);
+    mbar_init(smem_u32(&bars->p_full), 128);
+    mbar_init(smem_u32(&bars->pv_done), 1);
     mbar_init(smem_u32(&bars->o_done), 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&bars->k_full[i]), 1);
@@ -131,309 +125,284 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<C::kTmemCols>(smem_u32(&bars->tmem_base));
+  if (warp == 5) {
+    tmem_alloc_cols<C::kTmemCols>(smem_u32(&bars->tmem_base));
+    if (C::kSplitP) tmem_alloc_cols<32>(smem_u32(&bars->tmem_p));
+    tmem_relinquish();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmemP = C::kSplitP ? bars->tmem_p : tmem + C::kColP;
 
   if (warp == 4) {
     // =============================== TMA producer ===============================
     // The whole warp walks the loop (waits are warp-wide), one elected lane issues the copies.
-    // Q and K are read through 3-D maps [rows, H, D] with a 64-wide box: columns >= D of a head are
-    // out of bounds and arrive as zeros, so the K padding of the MMA needs no patching.
-    int gk = 0, gv = 0, it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int qt = item % kQTiles, h = (item / kQTiles) % H, r = item / (kQTiles * H);
-      const int qb = it % QB;
-      if (it >= QB) mbar_wait(smem_u32(&bars->q_empty[qb]), ((it / QB) - 1) & 1);
-      if (elect_one()) {
-        mbar_expect_tx(smem_u32(&bars->q_full[qb]), C::kQBytes);
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&bars->q_full), C::kQBytes);
 #pragma unroll
-        for (int kb = 0; kb < C::kKBlocks; ++kb)
-          tma_load_3d(sQ + qb * C::kQBytes + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM,
-                      smem_u32(&bars->q_full[qb]));
-      }
-      for (int lt = 0; lt <= total; ++lt) {
-        if (lt < total) {       // K tile lt (runs one tile ahead of V)
-          const int p = lt / C::kTiles, j = lt % C::kTiles;
-          const int rr = partner[p * R + r];
-          const int st = gk % KS;
-          if (gk >= KS) mbar_wait(smem_u32(&bars->k_empty[st]), ((gk / KS) - 1) & 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
+      for (int kb = 0; kb < C::kKBlocks; ++kb)
+        tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
+    }
+    for (int lt = 0; lt <= total; ++lt) {
+      if (lt < total) {       // K tile lt (runs one tile ahead of V)
+        const int p = lt / C::kTiles, j = lt % C::kTiles;
+        const int rr = partner[p * R + r];
+        const int st = lt % C::kKStages;
+        if (lt >= C::kKStages) mbar_wait(smem_u32(&bars->k_empty[st]), ((lt / C::kKStages) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
 #pragma unroll
-            for (int kb = 0; kb < C::kKBlocks; ++kb)
-              tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &tmK, kb * 64, h, rr * N + j * kTileN,
-                          smem_u32(&bars->k_full[st]));
-          }
-          ++gk;
+          for (int kb = 0; kb < C::kKBlocks; ++kb)
+            tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &tmK, kb * 64, h, rr * N + j * kTileN,
+                        smem_u32(&bars->k_full[st]));
         }
-        if (lt >= 1) {          // V^T tile lt-1
-          const int lv = lt - 1;
-          const int p = lv / C::kTiles, j = lv % C::kTiles;
-          const int rr = partner[p * R + r];
-          const int st = gv % VS;
-          if (gv >= VS) mbar_wait(smem_u32(&bars->v_empty[st]), ((gv / VS) - 1) & 1);
-          if (elect_one()) {
-            mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
-            tma_load_2d(sV + st * C::kVBytes, &tmV, j * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
-          }
-          ++gv;
-        }
-        __syncwarp();
       }
+      if (lt >= 1) {          // V^T tile lt-1
+        const int lv = lt - 1;
+        const int p = lv / C::kTiles, j = lv % C::kTiles;
+        const int rr = partner[p * R + r];
+        const int st = lv % C::kVStages;
+        if (lv >= C::kVStages) mbar_wait(smem_u32(&bars->v_empty[st]), ((lv / C::kVStages) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
+          tma_load_2d(sV + st * C::kVBytes, &tmV, j * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
+        }
+      }
+      __syncwarp();
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================
-    // Stream step s issues Q K^T of tile s (into S[s & 1], as soon as the softmax warps have pulled
-    // tile s-2 out of it) and then P V of tile s-2.  tcgen05.mma executes in issue order, so the
-    // score MMAs of the next two tiles are always queued ahead of the P V that waits for the softmax.
-    const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_tiles = n_my * total;
-    int it_q = 0, j_q = 0;     // item / tile-in-item of the QK cursor
-    int j_p = 0;               // tile-in-item of the PV cursor
-    for (int s = 0; s < n_tiles + 2; ++s) {
-      // DBG build: clock64 stamps of the first 64 stream steps, int64 [2, grid, 64, 8] behind the S dump
-      long long* ms = nullptr;
-      if (DBG && s < 64 && lane == 0)
-        ms = reinterpret_cast<long long*>(dbg + (size_t)n_items * kBlockM * kTileN) + ((size_t)(gridDim.x + blockIdx.x) * 64 + s) * 8;
-      if (DBG && ms) ms[0] = clock64();
-      if (s < n_tiles) {
-        const int qb = it_q % QB, st = s % KS, sb = s & 1;
-        if (j_q == 0) mbar_wait(smem_u32(&bars->q_full[qb]), (it_q / QB) & 1);
-        mbar_wait(smem_u32(&bars->k_full[st]), (s / KS) & 1);
-        if (s >= 2) mbar_wait(smem_u32(&bars->s_free[sb]), ((s >> 1) - 1) & 1);
-        tc_fence_after();
-        if (DBG && ms) ms[1] = clock64();
-        if (elect_one()) {
+    // P in its own columns: QK(j+1) is issued as soon as the softmax warps have read S_j (s_free),
+    // i.e. it runs under the softmax of tile j; PV(j) follows when P_j is complete.
+    // P aliased on S (d=160): QK(j+1) has to follow PV(j) (tcgen05.mma executes in issue order).
+    auto issue_qk = [&](int j) {
+      const int st = j % C::kKStages;
+      mbar_wait(smem_u32(&bars->k_full[st]), (j / C::kKStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < C::kKSteps; ++ks) {
-            const uint32_t qoff = qb * C::kQBytes + (ks >> 2) * kBlockM * 128 + (ks & 3) * 32;
-            const uint32_t koff = st * C::kKBytes + (ks >> 2) * kTileN * 128 + (ks & 3) * 32;
-            umma_ss(tmem + C::kColS + sb * kTileN, umma_desc_k_sw128(sQ + qoff), umma_desc_k_sw128(sK + koff), kIdescQK,
-                    ks > 0);
-          }
-          umma_commit(smem_u32(&bars->s_full[sb]));
-          umma_commit(smem_u32(&bars->k_empty[st]));
-          if (j_q == total - 1) umma_commit(smem_u32(&bars->q_empty[qb]));
+        for (int ks = 0; ks < C::kKSteps; ++ks) {
+          const uint32_t qoff = (ks >> 2) * kBlockM * 128 + (ks & 3) * 32;
+          const uint32_t koff = (ks >> 2) * kTileN * 128 + (ks & 3) * 32;
+          umma_ss(tmem + C::kColS, umma_desc_k_sw128(sQ + qoff), umma_desc_k_sw128(sK + st * C::kKBytes + koff),
+                  kIdescQK, ks > 0);
         }
-        __syncwarp();
-        if (++j_q == total) { j_q = 0; ++it_q; }
+        umma_commit(smem_u32(&bars->s_full));
+        umma_commit(smem_u32(&bars->k_empty[st]));
+      }
+      __syncwarp();
+    };
+    mbar_wait(smem_u32(&bars->q_full), 0);
+    issue_qk(0);
+    for (int j = 0; j < total; ++j) {
+      const int st = j % C::kVStages;
+      // DBG build: MMA-warp stamps, int64 [grid,32,8] behind the softmax stamps
+      long long* ms = nullptr;
+      if (DBG && j < 32 && lane == 0)
+        ms = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kTileN) + ((size_t)(gridDim.x + blockIdx.x) * 32 + j) * 8;
+      if (DBG && ms) ms[0] = clock64();
+      if (!C::kAliasP && j + 1 < total) {
+        mbar_wait(smem_u32(&bars->s_free), j & 1);
+        if (DBG && ms) ms[1] = clock64();
+        issue_qk(j + 1);
       }
       if (DBG && ms) ms[2] = clock64();
-      if (s >= 2) {
-        const int g = s - 2;
-        const int st = g % VS, pb = g % PB;
-        mbar_wait(smem_u32(&bars->v_full[st]), (g / VS) & 1);
-        mbar_wait(smem_u32(&bars->p_full[pb]), (g / PB) & 1);
-        tc_fence_after();
-        if (DBG && ms) ms[3] = clock64();
-        if (elect_one()) {
+      mbar_wait(smem_u32(&bars->v_full[st]), (j / C::kVStages) & 1);
+      mbar_wait(smem_u32(&bars->p_full), j & 1);
+      tc_fence_after();
+      if (DBG && ms) ms[3] = clock64();
+      if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kTileN / 16; ++ks)
-            umma_ts(tmem + C::kColO, tmem + C::kColP + pb * (kTileN / 2) + ks * 8,
-                    umma_desc_k_sw128(sV + st * C::kVBytes + ks * 32), kIdescPV, (j_p > 0) || (ks > 0));
-          umma_commit(smem_u32(&bars->p_free[pb]));
-          umma_commit(smem_u32(&bars->v_empty[st]));
-          if (j_p == total - 1) umma_commit(smem_u32(&bars->o_done));
-        }
-        __syncwarp();
-        if (++j_p == total) j_p = 0;
+        for (int ks = 0; ks < kTileN / 16; ++ks)
+          umma_ts(tmem + C::kColO, tmemP + ks * 8, umma_desc_k_sw128(sV + st * C::kVBytes + ks * 32), kIdescPV,
+                  (j > 0) || (ks > 0));
+        umma_commit(smem_u32(&bars->pv_done));
+        if (j == total - 1) umma_commit(smem_u32(&bars->o_done));
+        umma_commit(smem_u32(&bars->v_empty[st]));
       }
+      __syncwarp();
+      if (C::kAliasP && j + 1 < total) issue_qk(j + 1);
       if (DBG && ms) ms[4] = clock64();
     }
   } else {
     // =============================== softmax warps ==============================
     const int tid = threadIdx.x;                       // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint32_t tO = tmem + lane_off + C::kColO;
+    const uint32_t tS = tmem + lane_off + C::kColS, tO = tmem + lane_off + C::kColO, tP = tmemP + lane_off;
+    int n = qt * kBlockM + tid;
+    const bool row_valid = n < N;
+    if (!row_valid) n = N - 1;
+    const float xq = pixel_centre(n % FEAT, step), yq = pixel_centre(n / FEAT, step);
     const float off = (step - 1.0f) * 0.5f;
     const float scale_log2 = kLog2e * rsqrtf((float)D);
+
+    // bias geometry of this thread's query pixel, base-2 units (already scaled by w_r * log2e / |l_q|):
+    //   t(key) = As * col + Bs * row + base,   bias = min(band' - |t|, 0) = min(band' - t, band' + t, 0)
+    float As = 0.f, Bs = 0.f, base = 0.f, bandp = 0.f;
+    float m_used = 0.f;                   // running reference maximum (set by the first half tile)
+    float bias_ub = 0.f;                  // upper bound of this query's bias over ALL keys of the first partner
     const uint64_t scale2 = pack2(scale_log2, scale_log2);
 
-    // O[:, 0:D] / O[:, D]  ->  out row (item `oit` of this CTA; its last P V signals o_done phase oit & 1)
-    auto epilogue = [&](int oit, __nv_bfloat16* orow, bool valid) {
-      mbar_wait(smem_u32(&bars->o_done), oit & 1);
+    for (int j = 0; j < total; ++j) {
+      const int p = j / C::kTiles, jj = j % C::kTiles;
+      if (jj == 0 && rowp != nullptr) {
+        const float* P = rowp + (size_t)(p * R + r) * CVD_ROWP_STRIDE;
+        const float a = fmaf(P[1], yq, P[0] * xq) + P[2];
+        const float b = fmaf(P[4], yq, P[3] * xq) + P[5];
+        const float c = fmaf(P[7], yq, P[6] * xq) + P[8];
+        const float k1 = P[10] * kLog2e / (sqrtf(a * a + b * b) + 1e-6f);
+        const float A = a * k1, B = b * k1;
+        As = A * step;
+        Bs = B * step;
+        base = fmaf(A, off, fmaf(B, off, c * k1));
+        bandp = P[9] * P[10] * kLog2e;
+        if (j == 0) {
+          // |t| is convex, so its minimum over the key grid is bounded below by 0 if the corner values
+          // change sign and by the smallest corner value otherwise: bias <= min(band' - tmin, 0).
+          const float e = (float)(FEAT - 1);
+          const float t00 = base, t10 = fmaf(As, e, base), t01 = fmaf(Bs, e, base), t11 = fmaf(As, e, t01);
+          const float lo = fminf(fminf(t00, t10), fminf(t01, t11)), hi = fmaxf(fmaxf(t00, t10), fmaxf(t01, t11));
+          const float tmin = (lo <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo), fabsf(hi));
+          bias_ub = fminf(bandp - tmin, 0.f);
+        }
+      }
+      // DBG build: clock64 stamps of thread 0 at the hand-off points, behind the S dump: int64 [grid,32,8]
+      long long* stamps = nullptr;
+      if (DBG && tid == 0 && j < 32)
+        stamps = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kTileN) + ((size_t)blockIdx.x * 32 + j) * 8;
+      if (DBG && stamps) stamps[0] = clock64();
+      mbar_wait(smem_u32(&bars->s_full), j & 1);
       tc_fence_after();
-      uint32_t lraw;
-      tmem_ld_x1(tO + D, lraw);
-      tmem_ld_wait();
-      const float inv = 1.0f / __uint_as_float(lraw);
+      if (DBG && stamps) stamps[1] = clock64();
+
+      uint32_t preg[kTileN / 2];
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 8) {
-        uint32_t o[8];
-        tmem_ld_x8(tO + c0, o);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t sreg[kHalfN];
+        tmem_ld_x32(tS + hh * kHalfN, sreg);
         tmem_ld_wait();
-        uint4 pk;
-        pk.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
-        pk.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
-        pk.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
-        pk.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        if (valid) *reinterpret_cast<uint4*>(orow + c0) = pk;
-      }
-    };
+        if (hh == 1 && !C::kAliasP) {      // S_j is in registers: the tensor core may start Q K_{j+1}^T
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bars->s_free));
+        }
+        if (DBG && j == 0) {
+          float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kTileN + hh * kHalfN;
+#pragma unroll
+          for (int c = 0; c < kHalfN; ++c) o[c] = __uint_as_float(sreg[c]);
+        }
+        // x = qk * log2e/sqrt(d) + bias - m_used, evaluated against the CURRENT reference maximum so
+        // the subtraction is free: min(band'-m - t, band'-m + t, -m) is one FMNMX3 per key, the two
+        // linear terms advance by one packed FADD2 per key pair, the score is one packed FFMA2.
+        const float bm = bandp - m_used, negm = -m_used;
+        const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
+        float xmax = -INFINITY;
+        uint64_t a1 = 0, a2 = 0;
+#pragma unroll
+        for (int c = 0; c < kHalfN; c += 2) {
+          const int cc = hh * kHalfN + c;      // key index inside the 64-key tile
+          if (cc % FEAT == 0 || c == 0) {      // start of a key-grid row (or of this half)
+            const float rb = fmaf(Bs, (float)(jj * kRowsPerTile + cc / FEAT), base);
+            const float t0 = fmaf(As, (float)(cc % FEAT), rb);
+            a1 = pack2(bm - t0, bm - t0 - As);
+            a2 = pack2(bm + t0, bm + t0 + As);
+          }
+          float a1x, a1y, a2x, a2y;
+          unpack2(a1, a1x, a1y);
+          unpack2(a2, a2x, a2y);
+          const float v0 = min3(a1x, a2x, negm), v1 = min3(a1y, a2y, negm);
+          float x0, x1;
+          unpack2(fma2(pack2(__uint_as_float(sreg[c]), __uint_as_float(sreg[c + 1])), scale2, pack2(v0, v1)), x0, x1);
+          if (N < kTileN && cc >= N) x0 = x1 = -INFINITY;   // keys past the row (N = 16): not in the softmax
+          xmax = max3(xmax, x0, x1);
+          sreg[c] = __float_as_uint(x0);
+          sreg[c + 1] = __float_as_uint(x1);
+          a1 = add2(a1, step1);
+          a2 = add2(a2, step2);
+        }
 
-    int g = 0, it = 0;
-    __nv_bfloat16* prev_orow = nullptr;
-    bool prev_valid = false;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int qt = item % kQTiles, h = (item / kQTiles) % H, r = item / (kQTiles * H);
-      int n = qt * kBlockM + tid;
-      const bool row_valid = n < N;
-      if (!row_valid) n = N - 1;
-      const float xq = pixel_centre(n % FEAT, step), yq = pixel_centre(n / FEAT, step);
-
-      // bias geometry of this thread's query pixel, base-2 units (already scaled by w_r * log2e / |l_q|):
-      //   t(key) = As * col + Bs * row + base,   bias = min(band' - |t|, 0) = min(band' - t, band' + t, 0)
-      float As = 0.f, Bs = 0.f, base = 0.f, bandp = 0.f;
-      float m_used = 0.f;                   // running reference maximum (set by the first half tile)
-      float bias_ub = 0.f;                  // upper bound of this query's bias over ALL keys of the first partner
-
-      for (int j = 0; j < total; ++j, ++g) {
-        const int p = j / C::kTiles, jj = j % C::kTiles;
-        if (jj == 0 && rowp != nullptr) {
-          const float* P = rowp + (size_t)(p * R + r) * CVD_ROWP_STRIDE;
-          const float a = fmaf(P[1], yq, P[0] * xq) + P[2];
-          const float b = fmaf(P[4], yq, P[3] * xq) + P[5];
-          const float c = fmaf(P[7], yq, P[6] * xq) + P[8];
-          const float k1 = P[10] * kLog2e / (sqrtf(a * a + b * b) + 1e-6f);
-          const float A = a * k1, B = b * k1;
-          As = A * step;
-          Bs = B * step;
-          base = fmaf(A, off, fmaf(B, off, c * k1));
-          bandp = P[9] * P[10] * kLog2e;
-          if (j == 0) {
-            // |t| is convex, so its minimum over the key grid is bounded below by 0 if the corner values
-            // change sign and by the smallest corner value otherwise: bias <= min(band' - tmin, 0).
-            const float e = (float)(FEAT - 1);
-            const float t00 = base, t10 = fmaf(As, e, base), t01 = fmaf(Bs, e, base), t11 = fmaf(As, e, t01);
-            const float lo = fminf(fminf(t00, t10), fminf(t01, t11)), hi = fmaxf(fmaxf(t00, t10), fmaxf(t01, t11));
-            const float tmin = (lo <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo), fabsf(hi));
-            bias_ub = fminf(bandp - tmin, 0.f);
+        // lazy maximum update (always on the very first half tile)
+        const bool first = (j == 0 && hh == 0);
+        const bool need = first || (xmax > kRescaleThreshold);
+        if (__any_sync(0xffffffffu, need)) {
+          if (!first) {
+            const float f = need ? ex2(-xmax) : 1.0f;
+            if (j > 0) {
+              // O holds tiles 0..j-1: PV(j-1) must have landed.  (s_full(j) implies PV(j-2) has completed,
+              // so this thread is at most one phase behind pv_done.)
+              mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int c0 = 0; c0 < C::kDV; c0 += 16) {
+                uint32_t o[16];
+                tmem_ld_x16(tO + c0, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                tmem_st_x16(tO + c0, o);
+              }
+            }
+            if (hh == 1) {   // the first half of P_j (still in registers) was computed against the old reference
+#pragma unroll
+              for (int i = 0; i < kHalfN / 2; ++i)
+                preg[i] = pack_bf16(__uint_as_float(preg[i] << 16) * f, __uint_as_float(preg[i] & 0xffff0000u) * f);
+            }
+          }
+          if (need) {
+            // First half tile: anchor the reference at the largest score this row can still reach through
+            // the bias (the epipolar band may lie many key rows ahead), so that approaching the band does
+            // not trigger a rescale every other tile.  Any reference >= the running maximum is valid.
+            const float shift = first ? fmaxf(xmax, bias_ub) : xmax;
+            m_used += shift;
+#pragma unroll
+            for (int c = 0; c < kHalfN; ++c) sreg[c] = __float_as_uint(__uint_as_float(sreg[c]) - shift);
           }
         }
-        const int sb = g & 1, pb = g % PB;
-        const uint32_t tS = tmem + lane_off + C::kColS + sb * kTileN;
-        long long* stamps = nullptr;
-        if (DBG && tid == 0 && g < 64)
-          stamps = reinterpret_cast<long long*>(dbg + (size_t)n_items * kBlockM * kTileN) + ((size_t)blockIdx.x * 64 + g) * 8;
-        if (DBG && stamps) stamps[0] = clock64();
-        mbar_wait(smem_u32(&bars->s_full[sb]), (g >> 1) & 1);
+#pragma unroll
+        for (int c = 0; c < kHalfN; c += 2)
+          preg[hh * (kHalfN / 2) + (c >> 1)] = pack_bf16(ex2(__uint_as_float(sreg[c])), ex2(__uint_as_float(sreg[c + 1])));
+        if (DBG && stamps) stamps[2 + hh] = clock64() + (long long)(preg[hh * 16] & 1u);
+      }
+      if (j > 0) {   // the P columns are free once PV(j-1) has read them (aliased mode: implied by s_full(j))
+        mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
         tc_fence_after();
-        if (DBG && stamps) stamps[1] = clock64();
-
-        uint32_t preg[kTileN / 2];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t sreg[kHalfN];
-          tmem_ld_x32(tS + hh * kHalfN, sreg);
-          tmem_ld_wait();
-          if (hh == 1) {      // S is in registers: the tensor core may overwrite this buffer with tile g+2
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->s_free[sb]));
-          }
-          if (DBG && j == 0) {
-            float* o = dbg + ((size_t)item * kBlockM + tid) * kTileN + hh * kHalfN;
-#pragma unroll
-            for (int c = 0; c < kHalfN; ++c) o[c] = __uint_as_float(sreg[c]);
-          }
-          // x = qk * log2e/sqrt(d) + bias - m_used, evaluated against the CURRENT reference maximum so
-          // the subtraction is free: min(band'-m - t, band'-m + t, -m) is one FMNMX3 per key, the two
-          // linear terms advance by one packed FADD2 per key pair, the score is one packed FFMA2.
-          const float bm = bandp - m_used, negm = -m_used;
-          const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
-          float xmax = -INFINITY;
-          uint64_t a1 = 0, a2 = 0;
-#pragma unroll
-          for (int c = 0; c < kHalfN; c += 2) {
-            const int cc = hh * kHalfN + c;      // key index inside the 64-key tile
-            if (cc % FEAT == 0 || c == 0) {      // start of a key-grid row (or of this half)
-              const float rb = fmaf(Bs, (float)(jj * kRowsPerTile + cc / FEAT), base);
-              const float t0 = fmaf(As, (float)(cc % FEAT), rb);
-              a1 = pack2(bm - t0, bm - t0 - As);
-              a2 = pack2(bm + t0, bm + t0 + As);
-            }
-            float a1x, a1y, a2x, a2y;
-            unpack2(a1, a1x, a1y);
-            unpack2(a2, a2x, a2y);
-            const float v0 = min3(a1x, a2x, negm), v1 = min3(a1y, a2y, negm);
-            float x0, x1;
-            unpack2(fma2(pack2(__uint_as_float(sreg[c]), __uint_as_float(sreg[c + 1])), scale2, pack2(v0, v1)), x0, x1);
-            if (N < kTileN && cc >= N) x0 = x1 = -INFINITY;   // keys past the row (N = 16): not in the softmax
-            xmax = max3(xmax, x0, x1);
-            sreg[c] = __float_as_uint(x0);
-            sreg[c + 1] = __float_as_uint(x1);
-            a1 = add2(a1, step1);
-            a2 = add2(a2, step2);
-          }
-
-          // lazy maximum update (always on the very first half tile of an item)
-          const bool first = (j == 0 && hh == 0);
-          const bool need = first || (xmax > kRescaleThreshold);
-          if (__any_sync(0xffffffffu, need)) {
-            if (!first) {
-              const float f = need ? ex2(-xmax) : 1.0f;
-              if (j > 0) {
-                // O holds tiles 0..j-1 of this item: P V of tile g-1 must have landed.
-                mbar_wait(smem_u32(&bars->p_free[(g - 1) % PB]), ((g - 1) / PB) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < C::kDV; c0 += 16) {
-                  uint32_t o[16];
-                  tmem_ld_x16(tO + c0, o);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                  tmem_st_x16(tO + c0, o);
-                }
-                tmem_st_wait();
-              }
-              if (hh == 1) {   // the first half of P (still in registers) was computed against the old reference
-#pragma unroll
-                for (int i = 0; i < kHalfN / 2; ++i)
-                  preg[i] = pack_bf16(__uint_as_float(preg[i] << 16) * f, __uint_as_float(preg[i] & 0xffff0000u) * f);
-              }
-            }
-            if (need) {
-              // First half tile: anchor the reference at the largest score this row can still reach through
-              // the bias (the epipolar band may lie many key rows ahead), so that approaching the band does
-              // not trigger a rescale every other tile.  Any reference >= the running maximum is valid.
-              const float shift = first ? fmaxf(xmax, bias_ub) : xmax;
-              m_used += shift;
-#pragma unroll
-              for (int c = 0; c < kHalfN; ++c) sreg[c] = __float_as_uint(__uint_as_float(sreg[c]) - shift);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < kHalfN; c += 2)
-            preg[hh * (kHalfN / 2) + (c >> 1)] = pack_bf16(ex2(__uint_as_float(sreg[c])), ex2(__uint_as_float(sreg[c + 1])));
-          if (DBG && stamps) stamps[2 + hh] = clock64() + (long long)(preg[hh * 16] & 1u);
-        }
-        // read-out of the previous item: its last P V completed while this tile's scores were computed, and
-        // the first P V of this item (which overwrites O) cannot start before p_full below.
-        if (j == 0 && it > 0) epilogue(it - 1, prev_orow, prev_valid);
-        if (g >= PB) {   // the P buffer is free once P V of tile g - PB has read it
-          mbar_wait(smem_u32(&bars->p_free[pb]), ((g / PB) - 1) & 1);
-          tc_fence_after();
-        }
-        if (DBG && stamps) stamps[4] = clock64();
-        tmem_st_x32(tmem + lane_off + C::kColP + pb * (kTileN / 2), preg);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->p_full[pb]));
-        if (DBG && stamps) stamps[5] = clock64();
       }
-      prev_orow = out + ((size_t)r * N + n) * (size_t)(H * D) + h * D;
-      prev_valid = row_valid;
+      if (DBG && stamps) stamps[4] = clock64();
+      tmem_st_x32(tP, preg);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->p_full));
+      if (DBG && stamps) stamps[5] = clock64();
     }
-    if (it > 0) epilogue(it - 1, prev_orow, prev_valid);
+
+    // epilogue: O[:, 0:D] / O[:, D]  ->  out[r, n, h*D : (h+1)*D]
+    mbar_wait(smem_u32(&bars->o_done), 0);   // committed once, after the last PV
+    tc_fence_after();
+    uint32_t lraw;
+    tmem_ld_x1(tO + D, lraw);
+    tmem_ld_wait();
+    const float inv = 1.0f / __uint_as_float(lraw);
+    __nv_bfloat16* orow = out + ((size_t)r * N + n) * (size_t)(H * D) + h * D;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 8) {
+      uint32_t o[8];
+      tmem_ld_x8(tO + c0, o);
+      tmem_ld_wait();
+      uint4 pk;
+      pk.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+      pk.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+      pk.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+      pk.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+      if (row_valid) *reinterpret_cast<uint4*>(orow + c0) = pk;
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem);
+    if (C::kSplitP) tmem_dealloc<32>(bars->tmem_p);
   }
 }
 
@@ -475,7 +444,8 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 
 // bf16 projections [rows, heads * d] seen as 3-D [rows, heads, d]; box [box_rows, 1 head, 64 columns], 128-byte
 // swizzle.  The 64-wide box is wider than a head for d < 64 (and its last box for d % 64 != 0): the columns past
-// d are out of bounds of the innermost dimension and are filled with zeros by the TMA unit.
+// d are out of bounds of the innermost dimension and are filled with zeros by the TMA unit, so the K padding of
+// the MMA needs no patching and no bytes of the neighbouring head are fetched.
 static int make_map_heads(CUtensorMap* m, const void* base, uint64_t rows, uint64_t heads, uint64_t d, uint32_t box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -510,10 +480,9 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
     CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured[dbg != nullptr] = true;
   }
-  const long long items = (long long)R * H * C::kQTiles;
-  CVD_REQUIRE(items > 0 && items < (1ll << 31), "cvd_epi_attn_fwd: %lld work items", items);
-  const long long resident = (long long)kNumSMs * C::kCtasPerSM;     // persistent: one CTA per residency slot
-  const long long grid = items < resident ? items : resident;
+  constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
+  const long long grid = (long long)R * H * kQTiles;
+  CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
   kern<<<(unsigned)grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, rowp, partner, (__nv_bfloat16*)out, R, H, n_partners,
                                                         S / (float)FEAT, dbg);
   CVD_LAUNCH_CHECK("epi_attn_fwd_kernel");
@@ -528,20 +497,21 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
   CVD_REQUIRE(N == feat * feat, "cvd_epi_attn_fwd: N=%d is not feat^2 (feat=%d); only square latents are supported", N, feat);
   CVD_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) & 15) == 0,
               "cvd_epi_attn_fwd: q/k/vt/out must be 16-byte aligned");
+  if (dbg == nullptr && feat <= 4) {   // 4x4 latent grid: warp-level kernel (a 128x64 tcgen05 tile would be 97 % padding; 6.5 vs 11 us)
+    const int rc = epi_attn_small_dispatch(q, k, vt, rowp, partner, out, R, heads, head_dim, n_partners, feat, S, st);
+    if (rc != -1000) return rc;
+  }
 #define CVD_CASE(D_, F_) \
   if (head_dim == D_ && feat == F_) return launch<D_, F_>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, dbg, st);
   CVD_CASE(40, 32)
   CVD_CASE(40, 64)
   CVD_CASE(80, 16)
   CVD_CASE(80, 32)
-  CVD_CASE(160, 8)
   CVD_CASE(160, 16)
-  CVD_CASE(160, 4)
   CVD_CASE(40, 16)
-  CVD_CASE(40, 8)
-  CVD_CASE(40, 4)
+  CVD_CASE(160, 8)
   CVD_CASE(80, 8)
-  CVD_CASE(80, 4)
+  CVD_CASE(40, 8)
 #undef CVD_CASE
   return fail(CVD_E_INVALID, "cvd_epi_attn_fwd: (head_dim=%d, feat=%d) is not an instantiated configuration", head_dim, feat);
 }

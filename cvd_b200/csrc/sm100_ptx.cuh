@@ -41,6 +41,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// non-blocking probe: never suspends the thread
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Wait of a warp that is not on the critical path: failed probes back off with nanosleep
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  uint32_t tries = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++tries > (1u << 22)) __trap();
+  }
+}
+// relaxed arrival: no release fence on the issuing thread (TMEM traffic is ordered by tcgen05.fence instead)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // One elected lane of a fully converged warp (elect.sync): the canonical guard for tcgen05.mma /
 // tcgen05.commit / TMA issue.  Unlike `if (lane == 0)` it lets ptxas predicate the uniform-datapath
 // instruction directly instead of wrapping every one in an election loop.
@@ -95,6 +121,12 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
+
+// Warpgroup-wide register re-allocation (all four warps of an aligned warpgroup execute the same one)
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
 // ---- UMMA descriptors ---------------------------------------------------------------------
 // Shared-memory operand, K-major, 128-byte swizzle (cute::UMMA::SmemDescriptor):

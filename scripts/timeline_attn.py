@@ -1,4 +1,5 @@
-"""Per-tile clock64 breakdown of the softmax and MMA warps (debug build of the bench-shape kernel)."""
+"""Hand-off latencies of the attention pipeline from clock64 stamps (what-if build, CVD_ATTN_VARIANT=11 skeleton
+or 12 full kernel; make -C cvd_b200/csrc EXTRA=-DCVD_ATTN_WHATIF)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,27 +19,40 @@ partner = torch.cat([torch.arange(R // 2, R), torch.arange(0, R // 2)]).to(torch
 rowp = ops.epi_row_params(Fm, feat, 256.0, None, _lib.FF_HORIZONTAL)
 items = R * H * (N // 128)
 grid = min(items, 148 * 2)
-buf = torch.zeros(items * 128 * 64 + 2 * grid * 64 * 8 * 2, device=dev, dtype=torch.float32)
+buf = torch.zeros(items * 128 * 64 + 2 * grid * 64 * 8 * 2 + grid * 4 * 16, device=dev, dtype=torch.float32)
 for _ in range(2):
     ops.epi_attn_fwd(q, k, vt, rowp, partner, H, 256.0, dbg_s=buf)
 torch.cuda.synchronize()
-allst = buf[items * 128 * 64:].view(torch.int64).view(2, grid, 64, 8).cpu().numpy()
-st = allst[0][:, 8:56, :6]
-mm = allst[1][:, 8:56, :5]
-names = ["wait s_full", "half0 ld+score+exp", "half1 ld+score+exp", "epilogue?+wait p_free", "P st+arrive"]
-d_ = np.diff(st, axis=2)
-gap = st[:, 1:, 0] - st[:, :-1, 5]
-print("softmax thread 0, stream tiles 8..55")
-for i, nm in enumerate(names):
-    print(f"  {nm:24s} mean={d_[:, :, i].mean():8.0f}  p50={np.percentile(d_[:, :, i], 50):8.0f}  p90={np.percentile(d_[:, :, i], 90):8.0f}")
-print(f"  loop gap                 mean={gap.mean():8.0f}")
-print(f"  per-tile period          mean={(st[:, -1, 0] - st[:, 0, 0]).mean() / (st.shape[1] - 1):8.0f}")
-md = np.diff(mm, axis=2)
-mnames = ["QK waits (q/k/s_free)", "QK issue (3 MMA + 2 commits)", "PV waits (v_full/p_full)", "PV issue (4 MMA + 2 commits)"]
-print("MMA warp, stream steps 8..55")
-for i, nm in enumerate(mnames):
-    print(f"  {nm:30s} mean={md[:, :, i].mean():8.0f}  p50={np.percentile(md[:, :, i], 50):8.0f}  p90={np.percentile(md[:, :, i], 90):8.0f}")
-print(f"  per-step period                mean={(mm[:, -1, 0] - mm[:, 0, 0]).mean() / (mm.shape[1] - 1):8.0f}")
-# lead of S over the softmax: time between QK issue of tile s and the softmax's wait for it
-lead = allst[0][:, 8:56, 0] - allst[1][:, 8:56, 2]
-print(f"  QK issued -> softmax asks for it: mean={lead.mean():8.0f} p10={np.percentile(lead, 10):8.0f}")
+tail = buf[items * 128 * 64:]
+allst = tail[:2 * grid * 64 * 8 * 2].view(torch.int64).view(2, grid, 64, 8).cpu().numpy().astype(np.float64)
+sm, mm = allst[0], allst[1]
+lo, hi = 10, 50
+def stat(name, x):
+    x = x[np.isfinite(x)]
+    print(f"  {name:58s} mean={x.mean():8.0f}  p10={np.percentile(x, 10):8.0f}  p50={np.percentile(x, 50):8.0f}  p90={np.percentile(x, 90):8.0f}")
+print("softmax thread 0 (stream tiles %d..%d)" % (lo, hi))
+stat("tile period", sm[:, lo + 1:hi + 1, 0] - sm[:, lo:hi, 0])
+stat("start -> first block issued", sm[:, lo:hi, 1] - sm[:, lo:hi, 0])
+stat("publish P(g-1) (wait p_free, st, fence, arrive)", sm[:, lo:hi, 2] - sm[:, lo:hi, 1])
+stat("-> S(g) released", sm[:, lo:hi, 3] - sm[:, lo:hi, 2])
+stat("second block issued", sm[:, lo:hi, 4] - sm[:, lo:hi, 3])
+stat("wait s_full(g+1)", sm[:, lo:hi, 5] - sm[:, lo:hi, 4])
+print("Q K^T issuer")
+stat("step period", mm[:, lo + 1:hi + 1, 0] - mm[:, lo:hi, 0])
+stat("waits (q/k/s_free)", mm[:, lo:hi, 1] - mm[:, lo:hi, 0])
+stat("issue 3 MMA + commits", mm[:, lo:hi, 2] - mm[:, lo:hi, 1])
+print("P V issuer")
+stat("waits (v_full/p_full)", mm[:, lo:hi, 5] - mm[:, lo:hi, 4])
+stat("issue 4 MMA + commits", mm[:, lo:hi, 6] - mm[:, lo:hi, 5])
+print("hand-offs")
+stat("S(g) released -> QK(g+2) waits satisfied", mm[:, lo + 2:hi + 2, 1] - sm[:, lo:hi, 3])
+stat("QK(g+2) issued -> softmax could see S(g+2) full (lower bound: asks later)", sm[:, lo + 1:hi + 1, 5] - mm[:, lo + 2:hi + 2, 2])
+stat("P(g-1) published -> PV(g-1) waits satisfied", mm[:, lo - 1:hi - 1, 5] - sm[:, lo:hi, 2])
+stat("QK(s) issued - tile s start (lead of the score MMA, >0 = late)", mm[:, lo:hi, 2] - sm[:, lo:hi, 0])
+if os.environ.get("CVD_ATTN_VARIANT") == "12":
+    acc = tail[2 * grid * 64 * 8 * 2:].view(torch.int32).view(grid, 4, 16).cpu().numpy().astype(np.float64)
+    tiles = acc[:, :, 8].mean()
+    print(f"softmax-side waits that really blocked (per warp, {tiles:.0f} tiles per CTA):")
+    for i, nm in enumerate(["s_full(g+1)", "p_free", "o_done"]):
+        print(f"  {nm:12s} blocked {acc[:, :, i].mean():7.1f} times, {acc[:, :, 4 + i].mean() / tiles:7.1f} cycles per tile;  by warp: " +
+              " ".join(f"{acc[:, w, i].mean():6.1f}/{acc[:, w, 4 + i].mean() / tiles:5.0f}" for w in range(4)))

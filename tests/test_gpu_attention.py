@@ -86,6 +86,9 @@ def test_qk_accumulator_dump(golden, dev):
     (32, 4, 80, 1, None, None),
     (32, 8, 80, 1, None, None),
     (32, 32, 40, 2, None, None),       # two partners, one softmax over 2N keys
+    (32, 8, 160, 2, None, None),       # small-grid (warp-level) kernel, two partners
+    (32, 4, 40, 2, None, 0.3),
+    (32, 8, 40, 1, None, 1.1),
     (16, 64, 40, 1, None, None),       # 512x512 images
 ])
 def test_tcgen05_kernel_vs_fp32(golden, dev, R, feat, d, kp, pair, theta):
