@@ -174,9 +174,56 @@ def temporal():
     save("temporal", **out)
 
 
+def _ref_lines(relpath, first, last):
+    """Source lines [first, last] (1-based, inclusive) of a reference file, dedented -- executed, never stored."""
+    import textwrap
+    with open(os.path.join(REF, relpath)) as fh:
+        lines = fh.readlines()[first - 1:last]
+    return textwrap.dedent("".join(lines))
+
+
+def sampler():
+    """Pins the sampler-side logic of the advanced pipeline by EXECUTING the reference's own lines:
+    camera rigs (inference_epi_advanced.py:110-128,297-345), the random view pairing and its CFG expansion
+    (pipelines/pipeline_animation_epi_advanced.py:622-633,651-652) and the per-call F loop (:639-645)."""
+    import math as _math
+    import types
+    from scipy.spatial.transform import Rotation as R, Slerp
+    from animatediff.data.dataset_validation import calc_fundamental_matrix
+    cam_fn_src = _ref_lines("inference_epi_advanced.py", 110, 128)
+    cam_src = _ref_lines("inference_epi_advanced.py", 297, 345)
+    pair_src = _ref_lines("animatediff/pipelines/pipeline_animation_epi_advanced.py", 622, 633)
+    floop_src = _ref_lines("animatediff/pipelines/pipeline_animation_epi_advanced.py", 639, 645)
+    cfg_src = _ref_lines("animatediff/pipelines/pipeline_animation_epi_advanced.py", 651, 652)
+    out = {}
+    for V, pattern in ((4, "circle"), (6, "upper_hemi")):
+        ns = {"np": np, "math": _math, "R": R, "Slerp": Slerp}
+        exec(cam_fn_src, ns)
+        ns["args"] = types.SimpleNamespace(view_num=V, video_length=16, image_width=256, image_height=256,
+                                           cam_pattern=pattern, camera_dist=0.5, cam_perturb_traj=0.0)
+        ns["c2ws_list"] = []
+        exec(cam_src, ns)
+        c2w = ns["c2ws_list"].astype(np.float32)          # the pipeline receives float32 tensors (:351-353)
+        Kf = ns["K_mats"].astype(np.float32)
+        out[f"v{V}_c2w"], out[f"v{V}_K"] = c2w, Kf
+        np.random.seed(1000 + V)
+        for call in range(3):
+            ps = {"np": np, "torch": torch, "video_split_num": V, "single_model_length": 16,
+                  "calc_fundamental_matrix": calc_fundamental_matrix, "aux_c2w": c2w, "aux_K_mats": Kf}
+            exec(pair_src, ps)
+            exec(floop_src, ps)
+            Fm = torch.cat(ps["F_mat_list"], dim=0).reshape(V, 16, 3, 3).float()
+            exec(cfg_src, ps)
+            out[f"v{V}_call{call}_video_id"] = ps["video_id"]
+            out[f"v{V}_call{call}_video_id_input"] = ps["video_id_input"]
+            out[f"v{V}_call{call}_F"] = Fm
+    save("sampler", **out)
+
+
 if __name__ == "__main__":
     Fm = geometry()
     bias(Fm)
     attention(Fm)
     module(Fm)
     temporal()
+    sampler()
