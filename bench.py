@@ -188,6 +188,69 @@ def workload_config(n_gpus):
             "l2_policy": "inputs larger than L2: distinct q/k/v^T buffers per call (1.9 GB per step)"}
 
 
+def denoise_bench(dev, world, rank, shard, peer, steps):
+    """The second half of the BASELINE metric on the path this repository owns: denoising steps/s of the sampler
+    loops (cvd_b200/sampler.py) on the hot-path skeleton UNet (cvd_b200/sync_unet.py: the 20 temporal + 20 epi
+    modules of the reference UNet at 256x256; the SD-1.5 spatial blocks are out of scope and NOT in this number).
+    One step = one CFG-batched UNet forward (R = 64 rows per GPU) + the DDIM update.  N = 1: the two-video loop on the
+    real pose pair; N > 1: the V = 2N-view loop (fresh pairing + device F recompute per call, partner rows over NVLink)."""
+    from cvd_b200 import sampler, sync_unet
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = sync_unet.SyncPathUNet().randomize_zero_init(1).to(dev).eval()
+    V_loc, V = 2, 2 * world
+    g = torch.Generator(device=dev).manual_seed(42)
+    lat = torch.randn(V_loc, 4, 16, 32, 32, device=dev, generator=g)
+    poses = [torch.randn(V_loc, c, 16, 32 >> i, 32 >> i, device=dev, generator=g) for i, c in enumerate(sync_unet.CHANNELS)]
+    sch = sampler.DDIMSchedule(device=dev)
+    if world == 1:
+        text = torch.randn(2, 77, 768, device=dev, generator=g)
+        Fm = golden_F().reshape(2, 16, 3, 3).to(dev)
+
+        # the whole UNet forward replays as ONE CUDA graph (about 1500 launches per forward otherwise); the timestep
+        # enters as a device scalar so that every step reuses the same graph
+        import cvd_b200
+        gnet = cvd_b200.GraphedModule(net)
+
+        def unet(x, t, **kw):
+            return gnet(x, torch.full((), float(t), device=dev), **kw)
+
+        def run(n, graphed=True):
+            return sampler.sample_pair(unet if graphed else net, lat, Fm, text, sch, n, 8.5, pose_embedding_features=poses)
+    else:
+        sampler.install_sharding(net, shard, peer)
+        text = torch.randn(2, 77, 768, device=dev, generator=g).repeat(V_loc, 1, 1)
+        c2w, K = sampler.multiview_cameras(V, 16, "circle", 0.5, 256)
+
+        def run(n):
+            return sampler.sample_multiview(net, lat, text, sch, n, 8.5, aux_c2w=c2w, aux_K_mats=K,
+                                            pose_embedding_features=poses, shard=shard)
+    with torch.no_grad():
+        run(3)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = run(steps)
+        e1.record()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        ms_eager = None
+        if world == 1:      # the same loop without the graph, for the record
+            run(2, graphed=False)
+            torch.cuda.synchronize()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            run(steps, graphed=False)
+            e3.record()
+            torch.cuda.synchronize()
+            ms_eager = e2.elapsed_time(e3) / steps
+    assert torch.isfinite(out).all()
+    return e0.elapsed_time(e1) / steps, V, ms_eager
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -357,11 +420,17 @@ def run_ours(args):
     barrier()
     ms_e2e = t0.elapsed_time(t1) / e_steps
 
+    # release the kernel-bench buffers before the UNet-level measurement
+    del bufs, land, layers, hosts, dev_in
+    torch.cuda.empty_cache()
+    ms_denoise, views, ms_eager = (None, 0, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
+
     # max over ranks
     if world > 1:
-        tt = torch.tensor([ms_value, ms_e2e, big_ms], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms_value, ms_e2e, big_ms, ms_denoise or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_value, ms_e2e, big_ms = (float(v) for v in tt.tolist())
+        ms_value, ms_e2e, big_ms, md = (float(v) for v in tt.tolist())
+        ms_denoise = md if ms_denoise is not None else None
     flops = step_flops(R_glob)
     big_flops = 4.0 * R * 1024 * 1024 * 320
     achieved = big_flops / (big_ms * 1e-3) / 1e12
@@ -387,6 +456,13 @@ def run_ours(args):
             "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                              "sample": f"oracle EpiSelfAttention.forward, 1 call per shape ({cb_flops / 1e9:.1f} GFLOP), best of 2"},
         }
+        if ms_denoise is not None:
+            line["denoise"] = {"steps_per_s": 1e3 / ms_denoise, "ms_per_step": ms_denoise, "views": views,
+                               "rows_per_gpu": R_PER_GPU, "guidance_scale": 8.5,
+                               "launch": "one CUDA graph per UNet forward" if world == 1 else "eager", "ms_per_step_eager": ms_eager,
+                               "unet": "hot-path skeleton cvd_b200.sync_unet.SyncPathUNet (20 temporal + 20 epi modules at "
+                                       "256x256; SD-1.5 spatial blocks excluded -- not comparable to a full-UNet number)",
+                               "loop": "sampler.sample_pair" if world == 1 else "sampler.sample_multiview (view-sharded)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -398,6 +474,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
                     help="N>1: pull partner rows over NVLink peer memory (default) or NCCL all-gather (baseline)")
     args = ap.parse_args()

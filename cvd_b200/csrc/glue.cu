@@ -2,6 +2,9 @@
 // GEGLU, residual updates and the inverse layout.  All kernels are coalesced on both the
 // read and the write side (layout changes go through a padded shared-memory tile), use
 // 8/16-byte vector accesses where the shape allows and warp-shuffle reductions.
+#include <cooperative_groups.h>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace cvd {
@@ -228,7 +231,23 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 // ---------------------------------------------------------------------------------------
 // GEGLU: out = h * gelu_erf(g), 8 bf16 (16 bytes) per thread.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+// Exact-form (erf) GELU of diffusers' GEGLU (F.gelu default).  erff() costs ~30 instructions and makes the kernel
+// compute-bound (65 % of the HBM roofline); here erfc(|z|) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),
+// t = 1 / (1 + p |z|) (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7, i.e. 2^-15 of the bf16 output's last bit) with
+// MUFU reciprocal / exp2 (rcp.approx / ex2.approx: ~1 ulp), and 1 + erf(z) is assembled without cancellation on the negative side.
+__device__ __forceinline__ float gelu_erf(float g) {
+  const float z = g * 0.70710678118654752f;
+  const float az = fabsf(z);
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * az * az));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * ex;   // erfc(|z|)
+  return 0.5f * g * (z < 0.f ? e : 2.0f - e);
+}
 
 __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ hg, uint4* __restrict__ out,
                                                     size_t tokens, int inner8) {
@@ -293,10 +312,170 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const uint4* __restrict_
   out[i] = ov;
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused GroupNorm + token layout for the fp32 residual stream: ONE read of x, ONE write of y.
+// A thread-block CLUSTER owns kFusedCB = 80 channels (8 / 4 / 2 whole groups at C = 320 / 640 /
+// 1280) of one frame; each of its CTAs takes 128 (or 64) pixels of them and keeps its 80 x 128
+// slab IN REGISTERS (10 independent float4 loads per thread, all in flight at once).  Per-channel
+// shifted sums meet in distributed shared memory (one cluster.sync), every CTA derives the group
+// statistics from all ranks' partials, normalises its registers, transposes them through a
+// conflict-free shared tile and writes 160-byte token segments.  The two-kernel version above
+// streams x twice and runs 10 240 eight-kilobyte CTAs for the layout pass.
+// ---------------------------------------------------------------------------------------
+constexpr int kFusedCB = 80;
+
+template <int PPL>   // pixels per lane: 4 (128 pixels per CTA, float4) or 2 (64 pixels, float2)
+__global__ void __launch_bounds__(256)
+groupnorm_tokens_fused_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              __nv_bfloat16* __restrict__ y, int C, int F, int HW, int groups, float eps, int layout,
+                              int csize) {
+  namespace cg = cooperative_groups;
+  constexpr int CB = kFusedCB, PX = 32 * PPL, PITCH = PX + 1, NCH = CB / 8;
+  extern __shared__ float gn_smem[];
+  float* tile = gn_smem;                       // [CB][PITCH], column of pixel p: (p % PPL) * 32 + p / PPL
+  float* psum = tile + CB * PITCH;             // [CB] this CTA's partial sums (read by the whole cluster)
+  float* psq = psum + CB;
+  float* cscale = psq + CB;
+  float* cshift = cscale + CB;
+  float* gsum = cshift + CB;                   // [8] per-group partials of this CTA (read by the whole cluster)
+  float* gsq = gsum + 8;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = blockIdx.x % csize;
+  const int item = blockIdx.x / csize;
+  const int nblk = C / CB;
+  const int cb = item % nblk;
+  const int f = (item / nblk) % F;
+  const int b = item / (nblk * F);
+  const int c0 = cb * CB;
+  const int cpg = C / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t cstride = (size_t)F * HW;
+  const float* base = x + (((size_t)b * C + c0) * F + f) * HW;      // channel c0 + c lives at base + c * cstride
+  const int p0 = rank * PX;
+
+  float v[NCH][PPL];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const float* src = base + (size_t)(warp + 8 * i) * cstride + p0 + lane * PPL;
+    if (PPL == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(src);
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][PPL - 1] = t.w;
+    } else {
+      const float2 t = *reinterpret_cast<const float2*>(src);
+      v[i][0] = t.x; v[i][1] = t.y;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = warp + 8 * i;
+    const float x0 = __ldg(base + (size_t)(c / cpg * cpg) * cstride);     // shift: first element of the group (conditioning)
+    float sm = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) {
+      const float d = v[i][k] - x0;
+      sm += d;
+      q = fmaf(d, d, q);
+    }
+    sm = warp_sum(sm);
+    q = warp_sum(q);
+    if (lane == 0) {
+      psum[c] = sm;
+      psq[c] = q;
+    }
+  }
+  __syncthreads();
+  const int ngrp = CB / cpg;                   // whole groups in this channel block (<= 8)
+  if (threadIdx.x < ngrp) {                    // this CTA's partial sums per GROUP: 2 * ngrp values cross the cluster
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < cpg; ++i) {
+      ts += psum[threadIdx.x * cpg + i];
+      tq += psq[threadIdx.x * cpg + i];
+    }
+    gsum[threadIdx.x] = ts;
+    gsq[threadIdx.x] = tq;
+  }
+  if (csize > 1) cluster.sync(); else __syncthreads();
+  if (threadIdx.x < CB) {
+    const int c = threadIdx.x, g = c / cpg;
+    float ts = 0.f, tq = 0.f;
+    if (csize > 1) {
+      for (int r = 0; r < csize; ++r) {
+        ts += cluster.map_shared_rank(gsum, r)[g];
+        tq += cluster.map_shared_rank(gsq, r)[g];
+      }
+    } else {
+      ts = gsum[g];
+      tq = gsq[g];
+    }
+    const float n = (float)cpg * (float)HW;
+    const float x0 = __ldg(base + (size_t)(g * cpg) * cstride);
+    const float md = ts / n;
+    const float rstd = rsqrtf(fmaxf(tq / n - md * md, 0.f) + eps);
+    const float sc = rstd * gamma[c0 + c];
+    cscale[c] = sc;
+    cshift[c] = beta[c0 + c] - (x0 + md) * sc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = warp + 8 * i;
+    const float sc = cscale[c], sh = cshift[c];
+#pragma unroll
+    for (int k = 0; k < PPL; ++k) tile[c * PITCH + k * 32 + lane] = fmaf(v[i][k], sc, sh);
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int e = threadIdx.x; e < PX * (CB / 2); e += 256) {
+    const int pl = e / (CB / 2), c2 = e % (CB / 2);
+    const int col = (pl % PPL) * 32 + pl / PPL;
+    const size_t o = token_of(b, f, p0 + pl, F, HW, layout) * C + c0 + 2 * c2;
+    *reinterpret_cast<__nv_bfloat162*>(y + o) =
+        __floats2bfloat162_rn(tile[(2 * c2) * PITCH + col], tile[(2 * c2 + 1) * PITCH + col]);
+  }
+  if (csize > 1) cluster.sync();    // no CTA may exit while a peer can still read its partial sums
+}
+
+template <int PPL>
+static int launch_groupnorm_fused(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int B, int C,
+                                  int F, int HW, int groups, float eps, int layout, cudaStream_t st) {
+  constexpr int PX = 32 * PPL;
+  const int csize = HW / PX;
+  const size_t smem = (size_t)(kFusedCB * (PX + 1) + 4 * kFusedCB + 16) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    CVD_CUDA(cudaFuncSetAttribute(groupnorm_tokens_fused_kernel<PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * F * (C / kFusedCB) * csize));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CVD_CUDA(cudaLaunchKernelEx(&cfg, groupnorm_tokens_fused_kernel<PPL>, x, gamma, beta, y, C, F, HW, groups, eps, layout, csize));
+  CVD_LAUNCH_CHECK("groupnorm_tokens_fused_kernel");
+  return CVD_OK;
+}
+
 template <typename T>
 static int launch_groupnorm_tokens(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B,
                                    int C, int F, int HW, int groups, float eps, int layout, cudaStream_t st) {
   const bool vec = (HW % Vec16<T>::N == 0) && (((uintptr_t)x & 15) == 0);
+  const int cpg = C / groups;
+  if (std::is_same<T, float>::value && vec && C % kFusedCB == 0 && kFusedCB % cpg == 0) {
+    // single pass over HBM, slab in registers (stats stays untouched: it is scratch of the two-kernel path)
+    const int cs4 = HW / 128, cs2 = HW / 64;
+    if (HW % 128 == 0 && (cs4 == 1 || cs4 == 2 || cs4 == 4 || cs4 == 8))
+      return launch_groupnorm_fused<4>((const float*)x, gamma, beta, (__nv_bfloat16*)y, B, C, F, HW, groups, eps, layout, st);
+    if (HW % 64 == 0 && (cs2 == 1 || cs2 == 2 || cs2 == 4 || cs2 == 8))
+      return launch_groupnorm_fused<2>((const float*)x, gamma, beta, (__nv_bfloat16*)y, B, C, F, HW, groups, eps, layout, st);
+  }
   if (vec)
     groupnorm_stats_kernel<T, true><<<B * F * groups, 256, 0, st>>>((const T*)x, stats, C, F, HW, groups, eps);
   else

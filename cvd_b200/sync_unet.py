@@ -39,7 +39,7 @@ MOTION_KWARGS = dict(num_attention_heads=8, num_transformer_block=1,
 def timestep_embedding(t, dim, device):
     half = dim // 2
     freq = torch.exp(-math.log(10000.0) * torch.arange(half, device=device, dtype=torch.float32) / half)
-    arg = float(t) * freq
+    arg = (t.to(device=device, dtype=torch.float32) if torch.is_tensor(t) else float(t)) * freq   # tensor: graph-capturable
     return torch.cat([torch.sin(arg), torch.cos(arg)])
 
 
