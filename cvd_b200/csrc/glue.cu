@@ -229,6 +229,68 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused residual update + LayerNorm: x += (y + bias) * scale (in place, fp32), n = LN(x) (+pe) -> bf16.
+// One warp per token, the row stays in registers: 12 bytes per element cross HBM instead of the 16 of
+// residual_add_kernel followed by layernorm_kernel.  y == nullptr: x += bias only (the deferred bias of
+// proj_in, whose GEMM writes fp32 directly).
+// ---------------------------------------------------------------------------------------
+template <int PAIRS>
+__global__ void __launch_bounds__(256)
+residual_layernorm_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ yin, const float* __restrict__ bias,
+                          float scale, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          const float* __restrict__ pe, __nv_bfloat16* __restrict__ n_out, int tokens, int seq_len, float eps) {
+  constexpr int C = PAIRS * 64;
+  const int lane = threadIdx.x & 31;
+  const size_t t = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= (size_t)tokens) return;
+  float2* row = reinterpret_cast<float2*>(x + t * C);
+  const __nv_bfloat162* yrow = yin ? reinterpret_cast<const __nv_bfloat162*>(yin + t * C) : nullptr;
+  const float2* bi = bias ? reinterpret_cast<const float2*>(bias) : nullptr;
+  float2 v[PAIRS];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = row[i];
+    float2 d = make_float2(0.f, 0.f);
+    if (yrow) d = __bfloat1622float2(yrow[i]);
+    if (bi) {
+      const float2 b = bi[i];
+      d.x += b.x;
+      d.y += b.y;
+    }
+    v[j].x = fmaf(d.x, scale, v[j].x);
+    v[j].y = fmaf(d.y, scale, v[j].y);
+    row[i] = v[j];
+    s += v[j].x + v[j].y;
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    const float dx = v[j].x - mean, dy = v[j].y - mean;
+    q = fmaf(dx, dx, fmaf(dy, dy, q));
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma);
+  const float2* b2 = reinterpret_cast<const float2*>(beta);
+  const float2* p2 = pe ? reinterpret_cast<const float2*>(pe + (t % seq_len) * C) : nullptr;
+  __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(n_out + t * C);
+#pragma unroll
+  for (int j = 0; j < PAIRS; ++j) {
+    const int i = lane + 32 * j;
+    const float2 g = g2[i], b = b2[i];
+    float ox = (v[j].x - mean) * rstd * g.x + b.x, oy = (v[j].y - mean) * rstd * g.y + b.y;
+    if (p2) {
+      const float2 p = p2[i];
+      ox += p.x;
+      oy += p.y;
+    }
+    out[i] = __floats2bfloat162_rn(ox, oy);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // GEGLU: out = h * gelu_erf(g), 8 bf16 (16 bytes) per thread.
 // ---------------------------------------------------------------------------------------
 // Exact-form (erf) GELU of diffusers' GEGLU (F.gelu default).  erff() costs ~30 instructions and makes the kernel
@@ -567,6 +629,26 @@ extern "C" int cvd_layernorm_fwd(const float* x, const float* gamma, const float
     default: return fail(CVD_E_INVALID, "cvd_layernorm_fwd: C=%d not supported (64, 320, 640, 1280)", C);
   }
   CVD_LAUNCH_CHECK("layernorm_kernel");
+  return CVD_OK;
+}
+
+extern "C" int cvd_residual_layernorm_fwd(float* x, const void* y, const float* bias, float scale, const float* gamma,
+                                          const float* beta, const float* pe, void* n_out, int tokens, int C, int seq_len,
+                                          float eps, cvd_stream_t stream) {
+  CVD_REQUIRE(x && gamma && beta && n_out, "cvd_residual_layernorm_fwd: null pointer");
+  CVD_REQUIRE(tokens > 0 && seq_len > 0, "cvd_residual_layernorm_fwd: tokens=%d seq_len=%d", tokens, seq_len);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((tokens + 7) / 8);
+  const __nv_bfloat16* yy = (const __nv_bfloat16*)y;
+  __nv_bfloat16* o = (__nv_bfloat16*)n_out;
+  switch (C) {
+    case 64: residual_layernorm_kernel<1><<<grid, 256, 0, st>>>(x, yy, bias, scale, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 320: residual_layernorm_kernel<5><<<grid, 256, 0, st>>>(x, yy, bias, scale, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 640: residual_layernorm_kernel<10><<<grid, 256, 0, st>>>(x, yy, bias, scale, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    case 1280: residual_layernorm_kernel<20><<<grid, 256, 0, st>>>(x, yy, bias, scale, gamma, beta, pe, o, tokens, seq_len, eps); break;
+    default: return fail(CVD_E_INVALID, "cvd_residual_layernorm_fwd: C=%d not supported (64, 320, 640, 1280)", C);
+  }
+  CVD_LAUNCH_CHECK("residual_layernorm_kernel");
   return CVD_OK;
 }
 

@@ -51,7 +51,9 @@ class _WeightCache:
             self._c[key] = hit
         return hit[1]
 
-    def bf16(self, key, p):
+    def bf16(self, key, p, transpose=False):
+        if transpose:     # [out, in] -> [in, out] contiguous: the B operand of torch.mm(x, W^T)
+            return self.get(key, p, lambda t: t.detach().to(torch.bfloat16).t().contiguous())
         return self.get(key, p, lambda t: t.detach().to(torch.bfloat16).contiguous())
 
     def f32(self, key, p):
@@ -369,19 +371,28 @@ class EpiTransformerBlock(nn.Module):
         self.ff_norm = nn.LayerNorm(dim)
         self._w = _WeightCache()
 
-    def forward_stream(self, hs, F_mats, H_mats=None, cross_attention_kwargs: Dict[str, Any] = {}, want_bf16=False):
-        """In-place update of the fp32 residual stream ``hs`` [R,N,C]; returns (hs, bf16 copy | None, aux)."""
+    def forward_stream(self, hs, F_mats, H_mats=None, cross_attention_kwargs: Dict[str, Any] = {}, want_bf16=False,
+                       pending=None):
+        """In-place update of the fp32 residual stream ``hs`` [R,N,C]; returns (hs, bf16 copy | None, aux).
+
+        Every ``x = branch(norm(x)) + x`` / ``norm(x)`` pair of epi_module.py:254-268 is ONE kernel
+        (``cvd_residual_layernorm_fwd``): the update of the previous branch is applied while the row is in registers
+        for the next LayerNorm.  ``pending = (y | None, bias | None, scale)`` is an update the caller still owes the
+        stream (the deferred bias of ``proj_in``)."""
         w = self._w
         aux_all = []
+        y_prev, b_prev, s_prev = pending if pending is not None else (None, None, 1.0)
         for i, (attn, norm) in enumerate(zip(self.attention_blocks, self.norms)):
-            n = ops.layernorm(hs, w.f32(f"g{i}", norm.weight), w.f32(f"b{i}", norm.bias), norm.eps)
+            n = ops.residual_layernorm_(hs, y_prev, b_prev, s_prev, w.f32(f"g{i}", norm.weight), w.f32(f"b{i}", norm.bias),
+                                        norm.eps)
             y, aux = attn.attend(n, F_mats=F_mats, H_mats=H_mats, **cross_attention_kwargs)
             if y.shape[0] != hs.shape[0]:
                 raise RuntimeError("the reference's chunk branch dropped rows; the residual add cannot broadcast "
                                    "(the reference fails here too, epi_module.py:263)")
-            ops.residual_add_(hs, y, attn._w.f32("bo", attn.to_out[0].bias), 1.0 / attn.rescale_output_factor)
+            y_prev, b_prev, s_prev = y, attn._w.f32("bo", attn.to_out[0].bias), 1.0 / attn.rescale_output_factor
             aux_all.append(aux)
-        n = ops.layernorm(hs, w.f32("gf", self.ff_norm.weight), w.f32("bf", self.ff_norm.bias), self.ff_norm.eps)
+        n = ops.residual_layernorm_(hs, y_prev, b_prev, s_prev, w.f32("gf", self.ff_norm.weight),
+                                    w.f32("bf", self.ff_norm.bias), self.ff_norm.eps)
         y = self.ff.forward_tokens(n)
         hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
         return hs, hb, aux_all
@@ -441,11 +452,17 @@ class EpiTransformer3DModel(nn.Module):
             H_mats = H_mats.reshape(-1, 3, 3)
         g = ops.groupnorm_tokens(x, w.f32("gn_w", self.norm.weight), w.f32("gn_b", self.norm.bias), self.norm.num_groups,
                                  self.norm.eps, _lib.LAYOUT_BF_HW)
-        hs = F.linear(g, w.bf16("in_w", self.proj_in.weight), w.bf16("in_b", self.proj_in.bias)).float()
+        # proj_in writes the fp32 residual stream directly (no bf16 round trip, no conversion pass); its bias is owed
+        # to the stream and lands inside the first fused residual + LayerNorm kernel
+        hs = torch.mm(g.view(-1, g.shape[-1]), w.bf16("in_wt", self.proj_in.weight, transpose=True),
+                      out_dtype=torch.float32).view(g.shape[0], g.shape[1], -1)
+        pending = (None, w.f32("in_b32", self.proj_in.bias), 1.0)
         aux_all, hb = [], None
         last = len(self.transformer_blocks) - 1
         for i, block in enumerate(self.transformer_blocks):
-            hs, hb, aux = block.forward_stream(hs, F_mats, H_mats, cross_attention_kwargs, want_bf16=(i == last))
+            hs, hb, aux = block.forward_stream(hs, F_mats, H_mats, cross_attention_kwargs, want_bf16=(i == last),
+                                               pending=pending)
+            pending = None
             aux_all += aux
         if hb is None:
             hb = hs.to(torch.bfloat16)

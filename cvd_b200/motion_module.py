@@ -143,16 +143,21 @@ class TemporalTransformerBlock(nn.Module):
         self.ff_norm = nn.LayerNorm(dim)
         self._w = _WeightCache()
 
-    def forward_stream(self, hs, pose_feature=None, scale=None, want_bf16=False):
-        """hs: fp32 residual stream [T, F, C], updated in place."""
+    def forward_stream(self, hs, pose_feature=None, scale=None, want_bf16=False, pending=None):
+        """hs: fp32 residual stream [T, F, C], updated in place.  Each residual update is fused with the LayerNorm
+        that follows it (``cvd_residual_layernorm_fwd``); ``pending`` = (y | None, bias | None, scale) still owed to
+        the stream by the caller (the deferred bias of ``proj_in``)."""
         w = self._w
         frames = hs.shape[1]
+        y_prev, b_prev, s_prev = pending if pending is not None else (None, None, 1.0)
         for i, (attn, norm) in enumerate(zip(self.attention_blocks, self.norms)):
             pe = attn.pe_table(frames, hs.device)
-            n = ops.layernorm(hs, w.f32(f"g{i}", norm.weight), w.f32(f"b{i}", norm.bias), norm.eps, pe=pe, seq_len=frames)
+            n = ops.residual_layernorm_(hs, y_prev, b_prev, s_prev, w.f32(f"g{i}", norm.weight), w.f32(f"b{i}", norm.bias),
+                                        norm.eps, pe=pe, seq_len=frames)
             y = attn.attend(n, pose_feature, scale)
-            ops.residual_add_(hs, y, attn._w.f32("bo", attn.to_out[0].bias), 1.0 / attn.rescale_output_factor)
-        n = ops.layernorm(hs, w.f32("gf", self.ff_norm.weight), w.f32("bf", self.ff_norm.bias), self.ff_norm.eps)
+            y_prev, b_prev, s_prev = y, attn._w.f32("bo", attn.to_out[0].bias), 1.0 / attn.rescale_output_factor
+        n = ops.residual_layernorm_(hs, y_prev, b_prev, s_prev, w.f32("gf", self.ff_norm.weight),
+                                    w.f32("bf", self.ff_norm.bias), self.ff_norm.eps)
         y = self.ff.forward_tokens(n)
         hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
         return hs, hb
@@ -206,11 +211,15 @@ class TemporalTransformer3DModel(nn.Module):
             raise _lib.CvdError("pose_feature must be in video layout [B,C,F,h,w]")
         g = ops.groupnorm_tokens(x, w.f32("gn_w", self.norm.weight), w.f32("gn_b", self.norm.bias), self.norm.num_groups,
                                  self.norm.eps, _lib.LAYOUT_BHW_F)
-        hs = F.linear(g, w.bf16("in_w", self.proj_in.weight), w.bf16("in_b", self.proj_in.bias)).float()
+        # fp32 residual stream straight out of the proj_in GEMM; its bias lands in the first fused residual + LayerNorm
+        hs = torch.mm(g.view(-1, g.shape[-1]), w.bf16("in_wt", self.proj_in.weight, transpose=True),
+                      out_dtype=torch.float32).view(g.shape[0], g.shape[1], -1)
+        pending = (None, w.f32("in_b32", self.proj_in.bias), 1.0)
         hb = None
         last = len(self.transformer_blocks) - 1
         for i, block in enumerate(self.transformer_blocks):
-            hs, hb = block.forward_stream(hs, pose, scale, want_bf16=(i == last))
+            hs, hb = block.forward_stream(hs, pose, scale, want_bf16=(i == last), pending=pending)
+            pending = None
         if hb is None:
             hb = hs.to(torch.bfloat16)
         t = F.linear(hb, w.bf16("out_w", self.proj_out.weight))

@@ -126,6 +126,20 @@ def layernorm(x, gamma, beta, eps=1e-5, pe=None, seq_len=1):
     return y
 
 
+def residual_layernorm_(x, y, bias, scale, gamma, beta, eps=1e-5, pe=None, seq_len=1):
+    """x (fp32, in place) += (y (bf16 | None) + bias (fp32 | None)) * scale; returns LayerNorm(x) (+pe) as bf16."""
+    C = x.shape[-1]
+    tokens = x.numel() // C
+    n = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.call("cvd_residual_layernorm_fwd", _check(x, torch.float32, "x"),
+              None if y is None else _check(y, torch.bfloat16, "y"),
+              None if bias is None else _check(bias, torch.float32, "bias"), float(scale),
+              _check(gamma, torch.float32, "gamma"), _check(beta, torch.float32, "beta"),
+              None if pe is None else _check(pe, torch.float32, "pe"), n.data_ptr(), tokens, C, seq_len, float(eps), _stream())
+    _count()
+    return n
+
+
 def geglu(hg):
     """bf16 [..., 2*inner] -> bf16 [..., inner]: h * gelu_erf(g)."""
     inner = hg.shape[-1] // 2

@@ -112,6 +112,14 @@ int cvd_groupnorm_tokens_fwd(const void* x, int x_dtype, const float* gamma, con
 int cvd_layernorm_fwd(const float* x, const float* gamma, const float* beta, const float* pe,
                       void* y, int tokens, int C, int seq_len, float eps, cvd_stream_t stream);
 
+/* ---- a6: fused residual update + LayerNorm: x += (y + bias) * scale in place (fp32; y bf16 or NULL, bias
+ *      fp32[C] or NULL), then n_out = LayerNorm(x) (+pe) as bf16.  Replaces the `x = attn(norm(x)) + x` /
+ *      `norm(x)` pairs of EpiTransformerBlock / TemporalTransformerBlock (epi_module.py:254-268,
+ *      motion_module.py:449-459) with one pass over the residual stream. */
+int cvd_residual_layernorm_fwd(float* x, const void* y, const float* bias, float scale,
+                               const float* gamma, const float* beta, const float* pe, void* n_out,
+                               int tokens, int C, int seq_len, float eps, cvd_stream_t stream);
+
 /* ---- a6: GEGLU gate (diffusers FeedForward used at epi_module.py:248):
  *      out[t, i] = hg[t, i] * gelu_erf(hg[t, inner + i]),  hg bf16 [T, 2*inner] -> out bf16 [T, inner] */
 int cvd_geglu_fwd(const void* hg, void* out, int tokens, int inner, cvd_stream_t stream);

@@ -48,6 +48,28 @@ def test_layernorm(dev, C, with_pe):
     assert_close(y, ref, rel=4e-3, max_abs=2e-2, what="layernorm")
 
 
+@pytest.mark.parametrize("C", [320, 640, 1280, 64])
+@pytest.mark.parametrize("mode", ["full", "bias_only", "no_bias", "pe"])
+def test_residual_layernorm_fused(dev, C, mode):
+    """x += (y + bias) * scale in place, n = LN(x) (+pe): against the two separate torch ops."""
+    from cvd_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(37, 16, C, generator=g) * 3 + 1).to(dev)
+    y = None if mode == "bias_only" else torch.randn(37, 16, C, generator=g).to(dev).to(torch.bfloat16)
+    bias = None if mode == "no_bias" else torch.randn(C, generator=g).to(dev)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(dev)
+    pe = torch.randn(16, C, generator=g).to(dev) if mode == "pe" else None
+    scale = 1.0 if mode == "bias_only" else 0.7
+    upd = (0 if y is None else y.float()) + (0 if bias is None else bias)
+    x_ref = x + upd * scale
+    n_ref = F.layer_norm(x_ref, (C,), gamma, beta, 1e-5) + (0 if pe is None else pe)
+    n = ops.residual_layernorm_(x, y, bias, scale, gamma, beta, 1e-5, pe=pe, seq_len=16)
+    assert n.dtype == torch.bfloat16
+    assert torch.allclose(x, x_ref, rtol=1e-6, atol=1e-5)          # the fp32 stream itself is updated exactly
+    assert_close(n, n_ref, rel=4e-3, max_abs=2e-2, what="residual_layernorm")
+
+
 def test_geglu_and_residual(dev):
     from cvd_b200 import ops
     g = torch.Generator().manual_seed(2)
