@@ -17,8 +17,11 @@ sum 4*R*N*N*C = 15.32 GFLOP * R (softmax, bias and MMA padding excluded).
           prepass, fused attention, output projection, D2H of the result.
   --impl reference : the reference's CPU path (oracle port of EpiSelfAttention.forward, fp32,
           all host threads) on a bounded sample of the same step (one call per shape).
-At N > 1 the views shard across ranks (weak scaling: 64 rows per GPU, 2N views); every call
-all-gathers K and V^T over NCCL and the kernel indexes the gathered buffer.
+At N > 1 the views shard across ranks (weak scaling: 64 rows per GPU, 2N views); K and V^T live in
+symmetric memory and every call moves exactly its partner rows across NVLink after one device-side
+barrier -- by the copy engines in two row chunks, the attention of chunk 0 running under the
+transfer of chunk 1 (--exchange dma, default), by our pull kernel (--exchange peer), or as an NCCL
+all-gather of every rank's rows (--exchange allgather, the baseline).
 """
 import argparse
 import json
@@ -41,7 +44,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
-EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
+EXCHANGE = "NVLink copy engines, 2 row chunks under the attention"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -272,7 +275,7 @@ def run_ours(args):
         os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
-        if args.exchange == "peer":
+        if args.exchange in ("peer", "dma"):
             peer = sharding.PeerExchange(shard)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _lib.load()
@@ -304,7 +307,8 @@ def run_ours(args):
             else:   # K / V^T resident in symmetric memory: the peers pull their partner rows from here
                 k, pk, hk = peer.alloc((R, N, C), torch.bfloat16, dev)
                 vt, pv, hv = peer.alloc((R, HEADS, ops.dv_rows(d), N), torch.bfloat16, dev)
-                xk, xv = (pk, hk), (pv, hv)
+                xk = (pk, hk, [hk.get_buffer(r_, (R, N, C), torch.bfloat16) for r_ in range(world)])
+                xv = (pv, hv, [hv.get_buffer(r_, (R, HEADS, ops.dv_rows(d), N), torch.bfloat16) for r_ in range(world)])
             k.copy_(torch.randn(R, N, C, device=dev, generator=gen))
             vt.zero_()
             vt[:, :, :d] = torch.randn(R, HEADS, d, N, device=dev, generator=gen).to(torch.bfloat16)
@@ -316,6 +320,27 @@ def run_ours(args):
     ident = None if peer is None else peer.identity_index(R, dev)
     theta = torch.tensor([0.5], device=dev)
     big_events = []
+    main_stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream()
+    ev_b, ev_c = torch.cuda.Event(), [torch.cuda.Event() for _ in range(4)]
+    chunks, whole = [(0, R // 2), (R // 2, R)], [(0, R)]
+    quarters = [(i * R // 4, (i + 1) * R // 4) for i in range(4)]
+    runs = runs_whole = runs_q = None
+    if shard is not None:
+        # contiguous runs of the partner map per chunk: (dst_lo, dst_hi, source rank, source row)
+        ph = partner.cpu().numpy()
+
+        def runs_of(lo, hi):
+            rr, a = [], lo
+            for i in range(lo + 1, hi + 1):
+                if i == hi or ph[i] != ph[i - 1] + 1 or ph[i] // R != ph[a] // R:
+                    rr.append((a, i, int(ph[a]) // R, int(ph[a]) % R))
+                    a = i
+            return rr
+
+        runs = [runs_of(lo, hi) for lo, hi in chunks]
+        runs_q = [runs_of(lo, hi) for lo, hi in quarters]
+        runs_whole = runs_of(0, R)
 
     def value_step(record):
         for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
@@ -326,9 +351,33 @@ def run_ours(args):
                     ks, vs = k, vt
                 elif peer is None:            # baseline: NCCL all-gather of every rank's K and V^T
                     ks, vs = shard.gather_rows(k), shard.gather_rows(vt)
-                else:                         # one cross-rank barrier, then pull only the partner rows over NVLink
-                    # (pulling in row chunks on a side stream under the attention of the previous chunk was
-                    # measured slower: the pull kernel and the smaller attention grids compete for SMs)
+                elif args.exchange == "dma":
+                    # one cross-rank barrier, then the partner rows cross NVLink on the COPY ENGINES in two row chunks on a
+                    # side stream; the attention of chunk 0 runs under the transfer of chunk 1 (no SMs are spent on the pull)
+                    xk[1].barrier()
+                    ev_b.record(main_stream)
+                    with torch.cuda.stream(side_stream):
+                        side_stream.wait_event(ev_b)
+                        # small grids: one transfer, one attention launch (four 16-row chunks at 32x32 measured slower:
+                        # 6.28 vs 6.19 ms per step on 2 GPUs, the quarter-size attention grids lose more than the overlap gains)
+                        use = chunks if feat >= 16 else whole
+                        for c, (lo, hi) in enumerate(use):
+                            for (dlo, dhi, src_rank, slo) in (runs_q[c] if use is quarters else (runs[c] if use is chunks else runs_whole)):
+                                ld[0][dlo:dhi].copy_(xk[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
+                                ld[1][dlo:dhi].copy_(xv[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
+                            ev_c[c].record(side_stream)
+                    for c, (lo, hi) in enumerate(use):
+                        main_stream.wait_event(ev_c[c])
+                        if record and feat == SHAPES[0][0]:
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                            ops.epi_attn_fwd(q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
+                            e1.record()
+                            big_events.append((e0, e1, R / (hi - lo)))
+                        else:
+                            ops.epi_attn_fwd(q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
+                    continue
+                else:                         # one cross-rank barrier, then pull only the partner rows over NVLink (SM kernel)
                     ks = peer.pull(xk[0], xk[1], partner, ld[0], rows_per_src=R)
                     vs = ops.peer_gather_rows(xv[0], partner, ld[1], rows_per_src=R)
                     idx = ident
@@ -475,12 +524,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "allgather"],
-                    help="N>1: pull partner rows over NVLink peer memory (default) or NCCL all-gather (baseline)")
+    ap.add_argument("--exchange", default="dma", choices=["peer", "dma", "allgather"],
+                    help="N>1: pull partner rows over NVLink peer memory with our kernel (peer), with the copy engines in two "
+                         "row chunks overlapped with the attention (dma), or NCCL all-gather (baseline)")
     args = ap.parse_args()
     global EXCHANGE
     if args.exchange == "allgather":
         EXCHANGE = "NCCL all-gather"
+    if args.exchange == "peer":
+        EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
     if args.impl == "reference":
         run_reference(args)
     else:
