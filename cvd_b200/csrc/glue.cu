@@ -478,6 +478,10 @@ groupnorm_tokens_fused_kernel(const float* __restrict__ x, const float* __restri
     cshift[c] = beta[c0 + c] - (x0 + md) * sc;
   }
   __syncthreads();
+  // This CTA has read everything it needs from its peers (the values are in registers / local shared memory): signal
+  // it now, relaxed (nothing is published), and collect the peers' signals only before exiting -- a CTA must not exit
+  // while a peer can still read its partial sums, but nobody has to WAIT for that in the middle of the kernel.
+  if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
     const int c = warp + 8 * i;
@@ -494,7 +498,7 @@ groupnorm_tokens_fused_kernel(const float* __restrict__ x, const float* __restri
     *reinterpret_cast<__nv_bfloat162*>(y + o) =
         __floats2bfloat162_rn(tile[(2 * c2) * PITCH + col], tile[(2 * c2 + 1) * PITCH + col]);
   }
-  if (csize > 1) cluster.sync();    // no CTA may exit while a peer can still read its partial sums
+  if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 
 template <int PPL>

@@ -35,6 +35,16 @@ def bench(name, shape_note, nbytes, make, run, iters=20):
     for s in sets[:2]:
         run(s)
     torch.cuda.synchronize()
+    if os.environ.get("PROFILE_GLUE_EAGER") == "1":     # plain launches (for ncu); timings are then launch-rate bound
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            run(sets[i % n_sets])
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / iters * 1e3
+        rows.append(dict(kernel=name, shape=shape_note, bytes=nbytes, us=us, gbs=nbytes / us / 1e3, frac=nbytes / us / 1e3 / peak))
+        return
     # the launches replay from a CUDA graph so that the small shapes are not bounded by the Python call rate
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
