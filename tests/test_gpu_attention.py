@@ -149,3 +149,19 @@ def test_unsupported_shape_is_an_error(dev):
     partner = torch.tensor([1, 0], device=dev, dtype=torch.int32)
     with pytest.raises(CvdError):
         ops.epi_attn_fwd(q, q, vt, None, partner, 8, 256.0)
+
+
+def test_two_warpgroup_variant_forced(dev):
+    """The d = 40 two-warpgroup kernel serves feat >= 64 by default; CVD_ATTN_WG2=1 forces it at 32x32 and 16x16 too.
+    The switch is read once per process, so the parity cases are re-run in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CVD_ATTN_WG2_CHILD") == "1":
+        pytest.skip("already inside the forced-variant child")
+    env = dict(os.environ, CVD_ATTN_WG2="1", CVD_ATTN_WG2_CHILD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_attention.py"), "-m", "gpu",
+                          "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
