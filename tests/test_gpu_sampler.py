@@ -114,6 +114,63 @@ def test_multiview_ddim_latents_vs_oracle(dev):
     assert rel_l2(base, first["ref"]) > 5e-2
 
 
+def test_six_view_upper_hemi_accumulate_vs_oracle(dev):
+    """BASELINE config 4 in miniature: 6 views on the 'upper_hemi' rig, accumulate_step 2 (two pairings averaged per
+    step), multistep 2, one UNet level (4x4 latent: the warp-level attention kernel) -- final latents against the CPU oracle."""
+    import cvd_b200
+    from cvd_b200 import sampler
+    from oracle import sampler_oracle as SO
+    V, feat, steps, guidance = 6, 4, 2, 3.0
+    prod, twin = build_pair(dev, levels=1, seed=13)
+    c2w, K = sampler.multiview_cameras(V, 16, "upper_hemi", 0.5, 256)
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(V, 4, 16, feat, feat, generator=g)
+    text = (torch.randn(2, 77, 768, generator=g) * 0.5).repeat(V, 1, 1)
+    poses = [torch.randn(V, 320, 16, feat, feat, generator=g) * 0.5]
+    noises = [torch.randn(V, 4, 16, feat, feat, generator=g) for _ in range(steps)]
+    it = iter(noises)
+    np.random.seed(77)
+    with torch.no_grad():
+        ref = SO.sample_multiview(twin, lat.clone(), text, steps, guidance, c2w, K, poses, multistep=2, accumulate=2,
+                                  noise_fn=lambda shape: next(it))
+    it = iter(noises)
+    np.random.seed(77)
+    calls = {"n": 0}
+
+    def unet(x, t, **kw):
+        calls["n"] += 1
+        return prod(x, t, **kw)
+
+    with torch.no_grad():
+        out = sampler.sample_multiview(unet, lat.to(dev), text.to(dev), sampler.DDIMSchedule(device=dev), steps, guidance,
+                                       aux_c2w=c2w, aux_K_mats=K, pose_embedding_features=[p.to(dev) for p in poses],
+                                       multistep=2, accumulate_step=2, noise_fn=lambda shape: next(it).to(dev))
+    r = rel_l2(out.cpu(), ref)
+    print(f"6-view upper_hemi, accumulate 2: final latents rel-L2 {r:.3e} after {calls['n']} UNet calls")
+    assert calls["n"] == (2 + 1) * 2 and torch.isfinite(out).all() and r < 5e-2, r
+
+
+def test_graphed_unet_equals_eager(dev):
+    """One CUDA graph per UNet forward (what bench.py's denoise loop replays): same result as the eager modules,
+    timestep as a device scalar so that every step reuses the graph."""
+    import cvd_b200
+    prod, _ = build_pair(dev, levels=2, seed=21)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(4, 4, 16, 8, 8, device=dev, generator=g)
+    text = torch.randn(4, 77, 768, device=dev, generator=g)
+    Fm = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))["F_mats"]).reshape(2, 16, 3, 3)
+    Fm = torch.cat([Fm[:1], Fm[:1], Fm[1:], Fm[1:]]).to(dev)
+    poses = [torch.randn(4, c, 16, 8 >> i, 8 >> i, device=dev, generator=g) for i, c in enumerate((320, 640))]
+    gnet = cvd_b200.GraphedModule(prod)
+    with torch.no_grad():
+        for t in (961.0, 41.0):
+            tt = torch.full((), t, device=dev)
+            y_e = prod(x, tt, F_mats=Fm, encoder_hidden_states=text, pose_embedding_features=poses)
+            y_g = gnet(x, tt, F_mats=Fm, encoder_hidden_states=text, pose_embedding_features=poses).clone()
+            assert torch.equal(y_e, y_g), float((y_e - y_g).abs().max())
+    assert len(gnet._graphs) == 1
+
+
 def test_pair_ddim_latents_vs_oracle(dev):
     """Two-video loop (pipeline_animation_epi.py), real pose-pair geometry, swap-halves partner."""
     from cvd_b200 import sampler
