@@ -33,8 +33,8 @@
 
 namespace cvd {
 // csrc/epi_attn_small.cu: warp-level kernel for the N <= 64 grids; -1000 = not a small-grid configuration
-int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                            int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st);
+int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out,
+                            float* lse, int R, int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st);
 namespace sm100 {
 
 using namespace ptx;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<D, FEAT>::kMinBlocks)
 epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
                     const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R, int H, int n_partners,
-                    float step, float* __restrict__ dbg) {
+                    float step, float* __restrict__ dbg, float* __restrict__ lse) {
   using C = Cfg<D, FEAT>;
   constexpr int N = C::kN;
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
@@ -385,6 +385,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_ld_x1(tO + D, lraw);
     tmem_ld_wait();
     const float inv = 1.0f / __uint_as_float(lraw);
+    // base-2 log-sum-exp of the row's logits (scores * log2e/sqrt(d) + bias * log2e): what the backward pass needs
+    if (lse != nullptr && row_valid) lse[((size_t)r * H + h) * N + n] = m_used + log2f(__uint_as_float(lraw));
     __nv_bfloat16* orow = out + ((size_t)r * N + n) * (size_t)(H * D) + h * D;
 #pragma unroll
     for (int c0 = 0; c0 < D; c0 += 8) {
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kThreadsW, 2)
 epi_attn_fwd_wg2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
                         const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R, int H, int n_partners,
-                        float step) {
+                        float step, float* __restrict__ lse) {
   using C = CfgW<D, FEAT>;
   constexpr int N = C::kN;
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
@@ -694,8 +696,10 @@ epi_attn_fwd_wg2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tmem_ld_x1(tO0 + D, l0raw);
     tmem_ld_x1(tO1 + D, l1raw);
     tmem_ld_wait();
-    const float inv = 1.0f / fmaf(__uint_as_float(l0raw), f0, __uint_as_float(l1raw) * f1);
+    const float lsum = fmaf(__uint_as_float(l0raw), f0, __uint_as_float(l1raw) * f1);
+    const float inv = 1.0f / lsum;
     const float w0 = f0 * inv, w1 = f1 * inv;
+    if (lse != nullptr && row_valid && g == 0) lse[((size_t)r * H + h) * N + n] = mm + log2f(lsum);
     __nv_bfloat16* orow = out + ((size_t)r * N + n) * (size_t)(H * D) + h * D;
     // 8-column chunks of the output row, split between the two warpgroups
     constexpr int kChunks = D / 8, kHalfChunks = (kChunks + 1) / 2;
@@ -779,7 +783,7 @@ static int make_map_heads(CUtensorMap* m, const void* base, uint64_t rows, uint6
 
 template <int D, int FEAT>
 static int launch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                  int R_kv, int H, int n_partners, float S, float* dbg, cudaStream_t st) {
+                  int R_kv, int H, int n_partners, float S, float* dbg, float* lse, cudaStream_t st) {
   using C = Cfg<D, FEAT>;
   constexpr int N = FEAT * FEAT;
   CUtensorMap tmQ, tmK, tmV;
@@ -799,7 +803,7 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
   kern<<<(unsigned)grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, rowp, partner, (__nv_bfloat16*)out, R, H, n_partners,
-                                                        S / (float)FEAT, dbg);
+                                                        S / (float)FEAT, dbg, lse);
   CVD_LAUNCH_CHECK("epi_attn_fwd_kernel");
   return CVD_OK;
 }
@@ -807,7 +811,7 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
 
 template <int D, int FEAT>
 static int launch_wg2(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                      int R_kv, int H, int n_partners, float S, cudaStream_t st) {
+                      int R_kv, int H, int n_partners, float S, float* lse, cudaStream_t st) {
   using C = CfgW<D, FEAT>;
   constexpr int N = FEAT * FEAT;
   CUtensorMap tmQ, tmK, tmV;
@@ -825,7 +829,7 @@ static int launch_wg2(const void* q, const void* k, const void* vt, const float*
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
   epi_attn_fwd_wg2_kernel<D, FEAT><<<(unsigned)grid, kThreadsW, C::kSmemBytes, st>>>(tmQ, tmK, tmV, rowp, partner,
                                                                                   (__nv_bfloat16*)out, R, H, n_partners,
-                                                                                  S / (float)FEAT);
+                                                                                  S / (float)FEAT, lse);
   CVD_LAUNCH_CHECK("epi_attn_fwd_wg2_kernel");
   return CVD_OK;
 }
@@ -844,7 +848,8 @@ static int wg2_mode() {
 }
 
 static int dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                    int R_kv, int N, int heads, int head_dim, int n_partners, int feat, float S, float* dbg, cudaStream_t st) {
+                    int R_kv, int N, int heads, int head_dim, int n_partners, int feat, float S, float* dbg, float* lse,
+                    cudaStream_t st) {
   CVD_REQUIRE(q && k && vt && partner && out, "cvd_epi_attn_fwd: null pointer");
   CVD_REQUIRE(R > 0 && R_kv > 0 && heads > 0 && n_partners >= 1, "cvd_epi_attn_fwd: R=%d R_kv=%d heads=%d n_partners=%d", R, R_kv, heads,
               n_partners);
@@ -852,16 +857,16 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
   CVD_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) & 15) == 0,
               "cvd_epi_attn_fwd: q/k/vt/out must be 16-byte aligned");
   if (dbg == nullptr && feat <= 4) {   // 4x4 latent grid: warp-level kernel (a 128x64 tcgen05 tile would be 97 % padding; 6.5 vs 11 us)
-    const int rc = epi_attn_small_dispatch(q, k, vt, rowp, partner, out, R, heads, head_dim, n_partners, feat, S, st);
+    const int rc = epi_attn_small_dispatch(q, k, vt, rowp, partner, out, lse, R, heads, head_dim, n_partners, feat, S, st);
     if (rc != -1000) return rc;
   }
   if (dbg == nullptr && head_dim == 40 && (wg2_mode() == 1 || (wg2_mode() == -1 && feat >= 64))) {
-    if (feat == 32) return launch_wg2<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, st);
-    if (feat == 64) return launch_wg2<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, st);
-    if (feat == 16) return launch_wg2<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, st);
+    if (feat == 32) return launch_wg2<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
+    if (feat == 64) return launch_wg2<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
+    if (feat == 16) return launch_wg2<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
   }
 #define CVD_CASE(D_, F_) \
-  if (head_dim == D_ && feat == F_) return launch<D_, F_>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, dbg, st);
+  if (head_dim == D_ && feat == F_) return launch<D_, F_>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, dbg, lse, st);
   CVD_CASE(40, 32)
   CVD_CASE(40, 64)
   CVD_CASE(80, 16)
@@ -882,7 +887,17 @@ extern "C" int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, co
                                 void* out, int R, int R_kv, int N, int heads, int head_dim, int n_partners, int feat,
                                 float F_mat_size, cvd_stream_t stream) {
   return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr,
-                              (cudaStream_t)stream);
+                              nullptr, (cudaStream_t)stream);
+}
+
+// Same, additionally writing the base-2 log-sum-exp of every (row, head, query) -- the statistic the backward pass
+// (cvd_epi_attn_bwd) recomputes the probabilities from.  lse: fp32 [R, heads, N].
+extern "C" int cvd_epi_attn_fwd_lse(const void* q, const void* k, const void* vt, const float* rowp, const int* partner,
+                                    void* out, float* lse, int R, int R_kv, int N, int heads, int head_dim, int n_partners,
+                                    int feat, float F_mat_size, cvd_stream_t stream) {
+  CVD_REQUIRE(lse != nullptr, "cvd_epi_attn_fwd_lse: null lse");
+  return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr,
+                              lse, (cudaStream_t)stream);
 }
 
 // Bring-up aid: additionally dumps the raw Q K^T accumulator of key tile 0 of every CTA
@@ -891,5 +906,5 @@ extern "C" int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* 
                                       void* out, float* dbg_s, int R, int R_kv, int N, int heads, int head_dim,
                                       int n_partners, int feat, float F_mat_size, cvd_stream_t stream) {
   return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, dbg_s,
-                              (cudaStream_t)stream);
+                              nullptr, (cudaStream_t)stream);
 }

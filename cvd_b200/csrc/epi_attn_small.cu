@@ -40,7 +40,7 @@ template <int D, int FEAT, int KP>   // KP: partners whose keys are concatenated
 __global__ void __launch_bounds__(kWarps * 32)
 epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                       const __nv_bfloat16* __restrict__ vt, const float* __restrict__ rowp, const int* __restrict__ partner,
-                      __nv_bfloat16* __restrict__ out, int R, int H, float step) {
+                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int R, int H, float step) {
   constexpr int N = FEAT * FEAT;
   constexpr int kMBlocks = N / 16;                 // 16-row query blocks per (row, head)
   constexpr int kKSteps = (D + 15) / 16;           // k steps of Q K^T
@@ -151,6 +151,10 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
   const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  if (lse != nullptr && t == 0) {      // base-2 log-sum-exp per query row (backward pass)
+    lse[((size_t)r * H + h) * N + row0] = mx0 + log2f(sum0);
+    lse[((size_t)r * H + h) * N + row1] = mx1 + log2f(sum1);
+  }
 
   // ---- O = P V: the score accumulators are already laid out as the A operand; B from v^T [dim][key]
   __nv_bfloat16* o0 = out + ((size_t)r * N + row0) * C + h * D;
@@ -175,8 +179,8 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 }
 
 template <int D, int FEAT>
-static int launch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R, int H,
-                  int n_partners, float S, cudaStream_t st) {
+static int launch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, float* lse,
+                  int R, int H, int n_partners, float S, cudaStream_t st) {
   constexpr int N = FEAT * FEAT;
   const long long tasks = (long long)R * H * (N / 16);
   const long long grid = (tasks + kWarps - 1) / kWarps;
@@ -186,11 +190,11 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   if (n_partners == 1)
     epi_attn_small_kernel<D, FEAT, 1><<<(unsigned)grid, kWarps * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                               (const __nv_bfloat16*)vt, rowp, partner,
-                                                                              (__nv_bfloat16*)out, R, H, step);
+                                                                              (__nv_bfloat16*)out, lse, R, H, step);
   else
     epi_attn_small_kernel<D, FEAT, 2><<<(unsigned)grid, kWarps * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                                               (const __nv_bfloat16*)vt, rowp, partner,
-                                                                              (__nv_bfloat16*)out, R, H, step);
+                                                                              (__nv_bfloat16*)out, lse, R, H, step);
   CVD_LAUNCH_CHECK("epi_attn_small_kernel");
   return CVD_OK;
 }
@@ -199,10 +203,10 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
 
 // Returns CVD_OK / an error if (head_dim, feat) is a small-grid configuration, and -1000 if it is not
 // (the caller then uses the tcgen05 kernel).
-int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                            int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st) {
+int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out,
+                            float* lse, int R, int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st) {
 #define CVD_CASE(D_, F_) \
-  if (head_dim == D_ && feat == F_) return small::launch<D_, F_>(q, k, vt, rowp, partner, out, R, heads, n_partners, S, st);
+  if (head_dim == D_ && feat == F_) return small::launch<D_, F_>(q, k, vt, rowp, partner, out, lse, R, heads, n_partners, S, st);
   CVD_CASE(160, 4)
   CVD_CASE(80, 4)
   CVD_CASE(40, 4)

@@ -88,6 +88,71 @@ def epi_attn_fwd(q, k, vt, rowp, partner, heads, F_mat_size, dbg_s=None):
     return out
 
 
+def epi_attn_fwd_lse(q, k, vt, rowp, partner, heads, F_mat_size):
+    """:func:`epi_attn_fwd` that also returns lse fp32 [R,H,N] (base-2 log-sum-exp of every query row's logits)."""
+    R, R_kv, N, d, n_partners, feat = _attn_args(q, k, vt, rowp, partner, heads)
+    out = torch.empty_like(q)
+    lse = torch.empty(R, heads, N, device=q.device, dtype=torch.float32)
+    _lib.call("cvd_epi_attn_fwd_lse", _check(q, torch.bfloat16, "q"), _check(k, torch.bfloat16, "k"),
+              _check(vt, torch.bfloat16, "vt"), None if rowp is None else _check(rowp, torch.float32, "rowp"),
+              _check(partner, torch.int32, "partner"), out.data_ptr(), lse.data_ptr(), R, R_kv, N, heads, d, n_partners, feat,
+              float(F_mat_size), _stream())
+    _count()
+    return out, lse
+
+
+def epi_attn_bwd(q, k, v, rowp, partner, out, d_out, lse, heads, F_mat_size):
+    """Backward of the attention core (single partner).  q [R,N,C], k / v [R_kv,N,C] (natural layout), out / d_out [R,N,C]
+    bf16; lse from :func:`epi_attn_fwd_lse`.  Returns fp32 (dq [R,N,C], dk [R_kv,N,C], dv [R_kv,N,C])."""
+    R, N, C = q.shape
+    R_kv = k.shape[0]
+    d = C // heads
+    feat = int(round(N ** 0.5))
+    assert partner.shape[0] == R, "the backward supports one partner per row"
+    assert k.shape == v.shape == (R_kv, N, C) and out.shape == d_out.shape == q.shape and lse.shape == (R, heads, N)
+    dq = torch.zeros(R, N, C, device=q.device, dtype=torch.float32)
+    dk = torch.zeros(R_kv, N, C, device=q.device, dtype=torch.float32)
+    dv = torch.zeros(R_kv, N, C, device=q.device, dtype=torch.float32)
+    delta = torch.empty(R, heads, N, device=q.device, dtype=torch.float32)
+    _lib.call("cvd_epi_attn_bwd", _check(q, torch.bfloat16, "q"), _check(k, torch.bfloat16, "k"), _check(v, torch.bfloat16, "v"),
+              None if rowp is None else _check(rowp, torch.float32, "rowp"), _check(partner, torch.int32, "partner"),
+              _check(out, torch.bfloat16, "out"), _check(d_out, torch.bfloat16, "d_out"), _check(lse, torch.float32, "lse"),
+              delta.data_ptr(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), R, R_kv, N, heads, d, feat, float(F_mat_size),
+              _stream())
+    _count(2)
+    return dq, dk, dv
+
+
+def padded_vt(v, heads):
+    """v bf16 [R,N,C] -> v^T per head with the ones row, bf16 [R,H,DV,N] (the forward kernels' V layout)."""
+    R, N, C = v.shape
+    d = C // heads
+    vt = torch.zeros(R, heads, dv_rows(d), N, device=v.device, dtype=torch.bfloat16)
+    vt[:, :, :d] = v.view(R, N, heads, d).permute(0, 2, 3, 1)
+    vt[:, :, d] = 1.0
+    return vt
+
+
+class EpiAttnFunction(torch.autograd.Function):
+    """Differentiable epipolar attention core: forward = the tcgen05 kernel (+lse), backward = ``cvd_epi_attn_bwd``.
+    Inputs q, k, v bf16 [R,N,C] (k, v are indexed through ``partner``); the bias (rowp) has no gradient
+    (epi_module.py:329,393).  First building block of SURVEY.md section 8 row f3; the drop-in layers stay inference-only."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, rowp, partner, heads, F_mat_size):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out, lse = epi_attn_fwd_lse(q, k, padded_vt(v, heads), rowp, partner, heads, F_mat_size)
+        ctx.save_for_backward(q, k, v, out, lse, partner)
+        ctx.rowp, ctx.heads, ctx.S = rowp, heads, F_mat_size
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse, partner = ctx.saved_tensors
+        dq, dk, dv = epi_attn_bwd(q, k, v, ctx.rowp, partner, out, d_out.contiguous().to(torch.bfloat16), lse, ctx.heads, ctx.S)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None
+
+
 def epi_attn_fwd_simt(q, k, vt, rowp, partner, heads, F_mat_size, out_dtype=torch.float32):
     """CUDA-core cross-check of :func:`epi_attn_fwd` (tests only)."""
     R, R_kv, N, d, n_partners, feat = _attn_args(q, k, vt, rowp, partner, heads)

@@ -90,6 +90,22 @@ int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const f
                            int heads, int head_dim, int n_partners, int feat, float F_mat_size,
                            cvd_stream_t stream);
 
+/* ---- f3 (first CUDA path): forward with the statistic the backward needs, and the backward of the attention core.
+ *      Replaces autograd through EpiAttnProcessor (attention_processor.py:573-619) in train_epi_control.py:512-642; the
+ *      epipolar bias has no gradient (epi_module.py:329,393).
+ *      cvd_epi_attn_fwd_lse: as cvd_epi_attn_fwd, plus lse fp32 [R, heads, N] = log2 sum_k 2^(s_k log2e/sqrt(d) + bias_k log2e).
+ *      cvd_epi_attn_bwd: q [R,N,C], k / v [R_kv,N,C] bf16 in their NATURAL layout, out / d_out [R,N,C] bf16, rowp fp32
+ *      [R,12] or NULL, partner int32 [R] (single partner), lse from the forward; delta: fp32 workspace [R, heads, N];
+ *      dq [R,N,C], dk / dv [R_kv,N,C] fp32 are ACCUMULATED (zero-fill them first).  head_dim in {40, 80, 160},
+ *      N a multiple of 16. */
+int cvd_epi_attn_fwd_lse(const void* q, const void* k, const void* vt, const float* rowp,
+                         const int* partner, void* out, float* lse, int R, int R_kv, int N, int heads,
+                         int head_dim, int n_partners, int feat, float F_mat_size, cvd_stream_t stream);
+int cvd_epi_attn_bwd(const void* q, const void* k, const void* v, const float* rowp, const int* partner,
+                     const void* out, const void* d_out, const float* lse, float* delta, float* dq,
+                     float* dk, float* dv, int R, int R_kv, int N, int heads, int head_dim, int feat,
+                     float F_mat_size, cvd_stream_t stream);
+
 /* Same contract (out may be bf16 or fp32), plain CUDA-core fp32 kernel that follows the
  * reference's arithmetic literally (natural-log softmax, unrounded probabilities): the
  * on-device cross-check used by the tests at sizes where the CPU oracle is slow.  Any
