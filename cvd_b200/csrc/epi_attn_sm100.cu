@@ -42,7 +42,7 @@ using namespace ptx;
 constexpr int kBlockM = 128;   // queries per CTA (= TMEM lanes)
 constexpr int kTileN = 64;     // keys per TMA tile / MMA round
 constexpr int kHalfN = 32;     // scores a softmax thread holds in registers at a time
-constexpr int kThreads = 192;
+constexpr int kThreads = 160;   // warps 0-3 softmax | warp 4 TMA producer + MMA issuer + TMEM owner
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 16.0f;  // lazy rescale: only when a score exceeds the reference by > 2^16
 
@@ -83,7 +83,7 @@ struct Barriers {
   uint32_t tmem_base, tmem_p;
 };
 
-template <int D, int FEAT, bool DBG>
+template <int D, int FEAT, bool DBG, bool PIPE>
 __global__ void __launch_bounds__(kThreads, Cfg<D, FEAT>::kMinBlocks)
 epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
@@ -127,7 +127,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 4) {
+    __syncwarp();
     tmem_alloc_cols<C::kTmemCols>(smem_u32(&bars->tmem_base));
     if (C::kSplitP) tmem_alloc_cols<32>(smem_u32(&bars->tmem_p));
     tmem_relinquish();
@@ -139,43 +140,34 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmemP = C::kSplitP ? bars->tmem_p : tmem + C::kColP;
 
   if (warp == 4) {
-    // =============================== TMA producer ===============================
-    // The whole warp walks the loop (waits are warp-wide), one elected lane issues the copies.
-    if (elect_one()) {
-      mbar_expect_tx(smem_u32(&bars->q_full), C::kQBytes);
+    // ===================== TMA producer + MMA issuer (one warp) =====================
+    // Five warps per CTA: 3 CTAs = 15 warps per SM leave 128 registers per thread (18 warps: 96).  The whole warp walks
+    // the loop (waits are warp-wide), one elected lane issues.  Ring stages are refilled by the issuer itself right
+    // where their consumer MMA is known to have been issued long ago:
+    //   K(j + stages) after Q K_j^T (k_empty), before Q K_{j+1}^T is issued;  V(j - 1 + stages) after P V_{j-1}.
+    auto load_k = [&](int lt) {
+      const int p = lt / C::kTiles, jt = lt % C::kTiles;
+      const int rr = partner[p * R + r];
+      const int st = lt % C::kKStages;
+      if (elect_one()) {
+        mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
 #pragma unroll
-      for (int kb = 0; kb < C::kKBlocks; ++kb)
-        tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
-    }
-    for (int lt = 0; lt <= total; ++lt) {
-      if (lt < total) {       // K tile lt (runs one tile ahead of V)
-        const int p = lt / C::kTiles, j = lt % C::kTiles;
-        const int rr = partner[p * R + r];
-        const int st = lt % C::kKStages;
-        if (lt >= C::kKStages) mbar_wait(smem_u32(&bars->k_empty[st]), ((lt / C::kKStages) - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
-#pragma unroll
-          for (int kb = 0; kb < C::kKBlocks; ++kb)
-            tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &tmK, kb * 64, h, rr * N + j * kTileN,
-                        smem_u32(&bars->k_full[st]));
-        }
-      }
-      if (lt >= 1) {          // V^T tile lt-1
-        const int lv = lt - 1;
-        const int p = lv / C::kTiles, j = lv % C::kTiles;
-        const int rr = partner[p * R + r];
-        const int st = lv % C::kVStages;
-        if (lv >= C::kVStages) mbar_wait(smem_u32(&bars->v_empty[st]), ((lv / C::kVStages) - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
-          tma_load_2d(sV + st * C::kVBytes, &tmV, j * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
-        }
+        for (int kb = 0; kb < C::kKBlocks; ++kb)
+          tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &tmK, kb * 64, h, rr * N + jt * kTileN,
+                      smem_u32(&bars->k_full[st]));
       }
       __syncwarp();
-    }
-  } else if (warp == 5) {
-    // =============================== MMA issuer =================================
+    };
+    auto load_v = [&](int lv) {
+      const int p = lv / C::kTiles, jt = lv % C::kTiles;
+      const int rr = partner[p * R + r];
+      const int st = lv % C::kVStages;
+      if (elect_one()) {
+        mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
+        tma_load_2d(sV + st * C::kVBytes, &tmV, jt * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
+      }
+      __syncwarp();
+    };
     // P in its own columns: QK(j+1) is issued as soon as the softmax warps have read S_j (s_free),
     // i.e. it runs under the softmax of tile j; PV(j) follows when P_j is complete.
     // P aliased on S (d=160): QK(j+1) has to follow PV(j) (tcgen05.mma executes in issue order).
@@ -196,6 +188,15 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       __syncwarp();
     };
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&bars->q_full), C::kQBytes);
+#pragma unroll
+      for (int kb = 0; kb < C::kKBlocks; ++kb)
+        tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
+    }
+    __syncwarp();
+    for (int lt = 0; lt < C::kKStages && lt < total; ++lt) load_k(lt);
+    for (int lv = 0; lv < C::kVStages && lv < total; ++lv) load_v(lv);
     mbar_wait(smem_u32(&bars->q_full), 0);
     issue_qk(0);
     for (int j = 0; j < total; ++j) {
@@ -205,12 +206,20 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (DBG && j < 32 && lane == 0)
         ms = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kTileN) + ((size_t)(gridDim.x + blockIdx.x) * 32 + j) * 8;
       if (DBG && ms) ms[0] = clock64();
+      if (j + C::kKStages < total) {       // Q K_j^T has read its K stage: refill it
+        mbar_wait(smem_u32(&bars->k_empty[j % C::kKStages]), (j / C::kKStages) & 1);
+        load_k(j + C::kKStages);
+      }
       if (!C::kAliasP && j + 1 < total) {
         mbar_wait(smem_u32(&bars->s_free), j & 1);
         if (DBG && ms) ms[1] = clock64();
         issue_qk(j + 1);
       }
       if (DBG && ms) ms[2] = clock64();
+      if (j >= 1 && j - 1 + C::kVStages < total) {   // P V_{j-1} has read its V stage: refill it
+        mbar_wait(smem_u32(&bars->v_empty[(j - 1) % C::kVStages]), ((j - 1) / C::kVStages) & 1);
+        load_v(j - 1 + C::kVStages);
+      }
       mbar_wait(smem_u32(&bars->v_full[st]), (j / C::kVStages) & 1);
       mbar_wait(smem_u32(&bars->p_full), j & 1);
       tc_fence_after();
@@ -280,6 +289,101 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (DBG && stamps) stamps[1] = clock64();
 
       uint32_t preg[kTileN / 2];
+      if constexpr (PIPE) {
+        // Fused form: the tile is walked in four 16-key quarters and every score goes bias -> FFMA2 -> MUFU.EX2 in ONE
+        // straight-line block, so each ex2 depends on the arithmetic of its own element and ptxas interleaves the MUFU
+        // stream with the FADD2 / FMNMX3 / FFMA2 stream (a warp keeps both pipes busy by itself; with the vote between
+        // the two phases it ran them back to back: 15 vs 9 cycles per warp-column).  The reference-maximum vote FOLLOWS
+        // the exponentials: in the rare case that a score exceeds the reference by more than 2^16 the quarter's
+        // exponentials are recomputed against the new reference from the x values still in registers (exact for any
+        // magnitude), and everything older is rescaled as before.  The second half of S is fetched under block 0.
+        constexpr int kQ = 16;
+        uint32_t s0[kHalfN], s1[kHalfN];
+        tmem_ld_x32(tS, s0);
+        tmem_ld_wait();
+        if (DBG && j == 0) {
+          float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kTileN;
+#pragma unroll
+          for (int c = 0; c < kHalfN; ++c) o[c] = __uint_as_float(s0[c]);
+        }
+        const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t* cur = (q < 2 ? s0 : s1) + (q & 1) * kQ;                 // scores -> x of quarter q (in place)
+          if (q == 0) tmem_ld_x32(tS + kHalfN, s1);                          // lands under this block
+          const float bm = bandp - m_used, negm = -m_used;
+          float xmax = -INFINITY;
+          uint64_t a1 = 0, a2 = 0;
+#pragma unroll
+          for (int c = 0; c < kQ; c += 2) {
+            const int cc = q * kQ + c;           // key index inside the 64-key tile
+            if (cc % FEAT == 0 || c == 0) {      // start of a key-grid row (or of this quarter)
+              const float rb = fmaf(Bs, (float)(jj * kRowsPerTile + cc / FEAT), base);
+              const float t0 = fmaf(As, (float)(cc % FEAT), rb);
+              a1 = pack2(bm - t0, bm - t0 - As);
+              a2 = pack2(bm + t0, bm + t0 + As);
+            }
+            float a1x, a1y, a2x, a2y;
+            unpack2(a1, a1x, a1y);
+            unpack2(a2, a2x, a2y);
+            const float v0 = min3(a1x, a2x, negm), v1 = min3(a1y, a2y, negm);
+            float x0, x1;
+            unpack2(fma2(pack2(__uint_as_float(cur[c]), __uint_as_float(cur[c + 1])), scale2, pack2(v0, v1)), x0, x1);
+            if (N < kTileN && cc >= N) x0 = x1 = -INFINITY;   // keys past the row (N = 16): not in the softmax
+            xmax = max3(xmax, x0, x1);
+            preg[q * (kQ / 2) + (c >> 1)] = pack_bf16(ex2(x0), ex2(x1));
+            cur[c] = __float_as_uint(x0);
+            cur[c + 1] = __float_as_uint(x1);
+            a1 = add2(a1, step1);
+            a2 = add2(a2, step2);
+          }
+          if (q == 0) {
+            tmem_ld_wait_dep32(s1);
+            if (!C::kAliasP) {                  // S_j is in registers: the tensor core may start Q K_{j+1}^T
+              tc_fence_before();
+              mbar_arrive(smem_u32(&bars->s_free));
+            }
+            if (DBG && j == 0) {
+              float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kTileN + kHalfN;
+#pragma unroll
+              for (int c = 0; c < kHalfN; ++c) o[c] = __uint_as_float(s1[c]);
+            }
+          }
+          // lazy maximum update (always on the very first quarter)
+          const bool first = (j == 0 && q == 0);
+          const bool need = first || (xmax > kRescaleThreshold);
+          if (__any_sync(0xffffffffu, need)) {
+            if (!first) {
+              const float f = need ? ex2(-xmax) : 1.0f;
+              if (j > 0) {
+                mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < C::kDV; c0 += 16) {
+                  uint32_t o[16];
+                  tmem_ld_x16(tO + c0, o);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                  tmem_st_x16(tO + c0, o);
+                }
+              }
+              // the earlier quarters of P_j were computed against the old reference
+#pragma unroll
+              for (int i = 0; i < q * (kQ / 2); ++i)
+                preg[i] = pack_bf16(__uint_as_float(preg[i] << 16) * f, __uint_as_float(preg[i] & 0xffff0000u) * f);
+            }
+            // this quarter: exponentials again, against the new reference
+            const float shift = need ? (first ? fmaxf(xmax, bias_ub) : xmax) : 0.f;
+            m_used += shift;
+#pragma unroll
+            for (int c = 0; c < kQ; c += 2)
+              preg[q * (kQ / 2) + (c >> 1)] =
+                  pack_bf16(ex2(__uint_as_float(cur[c]) - shift), ex2(__uint_as_float(cur[c + 1]) - shift));
+          }
+          if (DBG && stamps && (q & 1)) stamps[2 + (q >> 1)] = clock64();
+        }
+      } else {
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t sreg[kHalfN];
@@ -366,6 +470,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           preg[hh * (kHalfN / 2) + (c >> 1)] = pack_bf16(ex2(__uint_as_float(sreg[c])), ex2(__uint_as_float(sreg[c + 1])));
         if (DBG && stamps) stamps[2 + hh] = clock64() + (long long)(preg[hh * 16] & 1u);
       }
+      }
       if (j > 0) {   // the P columns are free once PV(j-1) has read them (aliased mode: implied by s_full(j))
         mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
         tc_fence_after();
@@ -403,7 +508,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem);
     if (C::kSplitP) tmem_dealloc<32>(bars->tmem_p);
@@ -793,7 +898,15 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   if ((rc = make_map(&tmV, vt, (uint64_t)R_kv * H * C::kDV, (uint64_t)N, C::kDV)) != CVD_OK) return rc;
   constexpr bool kHasDebug = (D == 40 && FEAT == 32);   // the S-dump variant is built for the bench shape only
   CVD_REQUIRE(dbg == nullptr || kHasDebug, "cvd_epi_attn_fwd_debug: only (head_dim=40, feat=32) has a debug build");
-  auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug> : epi_attn_fwd_kernel<D, FEAT, false>;
+  // CVD_ATTN_PIPE=0 selects the un-pipelined softmax loop at the bench shape (A/B measurements only)
+  static int pipe = -1;
+  if (pipe < 0) {
+    const char* e = getenv("CVD_ATTN_PIPE");
+    pipe = (e != nullptr && e[0] == '0' && kHasDebug) ? 0 : 1;
+  }
+  auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug, true>
+                                            : (pipe ? epi_attn_fwd_kernel<D, FEAT, false, true>
+                                                    : epi_attn_fwd_kernel<D, FEAT, false, !kHasDebug>);
   static bool configured[2] = {false, false};   // one process per GPU: set the attribute once per kernel
   if (!configured[dbg != nullptr]) {
     CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));

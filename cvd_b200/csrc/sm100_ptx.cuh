@@ -168,6 +168,14 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 // ---- TMEM <-> registers (32 lanes x 32 bit, N consecutive columns per thread) -----------
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that names the destination registers of an earlier tcgen05.ld as in/out operands, so no use of them can be
+// scheduled above the wait when independent work sits between the load and the wait
+__device__ __forceinline__ void tmem_ld_wait_dep32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t addr, uint32_t& r) {
@@ -220,6 +228,18 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t addr, const uint32_t* r) {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile twins: asm volatile statements keep their relative order, which pins the interleaving of the MUFU stream
+// with the FMNMX stream in the software-pipelined softmax loop (ptxas otherwise batches all MUFUs first)
+__device__ __forceinline__ float ex2v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float min3v(float a, float b, float c) {
+  float y;
+  asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
   return y;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) {

@@ -60,6 +60,13 @@ class _WeightCache:
         return self.get(key, p, lambda t: t.detach().float().contiguous())
 
 
+def _wants_grad(module, *tensors):
+    """True where autograd expects a graph through this call (training step)."""
+    if not torch.is_grad_enabled():
+        return False
+    return module.training or any(t is not None and t.requires_grad for t in tensors)
+
+
 def _require_inference(module, *tensors):
     """Forward only: refuse to run where autograd would expect a graph."""
     if torch.is_grad_enabled() and (module.training or any(t is not None and t.requires_grad for t in tensors)):
@@ -334,11 +341,58 @@ class EpiSelfAttention(nn.Module):
         return self.processor(self, hidden_states, kv_index=kv_index, scale=scale, mono_direction=self.epi_mono_direction,
                               fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp, **kw)
 
+    def attend_train(self, n, F_mats=None, H_mats=None, **kw):
+        """Differentiable twin of :meth:`attend` + the to_out bias / rescale (train_epi_control.py:589-616 runs the
+        reference layer under autocast and calls loss.backward()).  Projections are torch bf16 GEMMs recorded by
+        autograd; the attention core is :class:`ops.EpiAttnFunction` (tcgen05 forward with log-sum-exp, cvd_epi_attn_bwd
+        backward, the bias recomputed in registers both ways -- it has no gradient, epi_module.py:329,393).
+        ``n`` bf16 [R,N,C] (LayerNorm output); returns (fp32 [R,N,C], None).  One partner per row."""
+        if H_mats is not None:
+            raise NotImplementedError("the H_mats (homography) branch (epi_module.py:301-310) is not built")
+        if self.epi_fix_firstframe or self.epi_mono_direction:
+            raise NotImplementedError("epi_fix_firstframe / epi_mono_direction are not built on the training path")
+        proc = self.processor
+        assert isinstance(proc, EpiAttnProcessor)   # epi_module.py:423
+        if proc.shard is not None or proc.peer is not None:
+            raise NotImplementedError("training is data-parallel over pairs (train_epi_control.py:349): both views of a "
+                                      "pair stay on one GPU, the view-sharded exchange is inference-only")
+        Fm, kv_index = (F_mats[0], F_mats[1]) if isinstance(F_mats, (list, tuple)) else (F_mats, None)
+        R, N, C = n.shape
+        rowp = None
+        if self.pos_encoder is not None and not self.epi_no_attention_mask:
+            if Fm is None:
+                raise NotImplementedError("F_mats=None (random pseudo lines on every row, epi_module.py:317-320) is not built")
+            rowp = self.pos_encoder.row_params(n, Fm)
+            if rowp.shape[0] != R:
+                raise NotImplementedError("the backward kernel takes one partner per row (2-view pairs, BASELINE config 5)")
+        if self.reference_chunk_quirk and rowp is not None and (R > 200 or N > 2048):
+            # epi_module.py:424-451 (see attend): tensor F_mats -> every row attends to ITSELF; list -> hidden[kv_index]
+            chunk = 128 * 1024 // max(1024, N)
+            if (R // chunk) * chunk != R:
+                raise RuntimeError("the reference's chunk branch dropped rows; the residual add cannot broadcast "
+                                   "(the reference fails here too, epi_module.py:263)")
+            partner = (torch.arange(R, device=n.device, dtype=torch.int32) if kv_index is None
+                       else proc.partner_index(R, kv_index, n.device))
+        else:
+            partner = proc.partner_index(R, kv_index, n.device)
+        if partner.shape[0] != R:
+            raise NotImplementedError("the backward kernel takes one partner per row (2-view pairs, BASELINE config 5)")
+        bf = torch.bfloat16
+        q = F.linear(n, self.to_q.weight.to(bf))
+        k = F.linear(n, self.to_k.weight.to(bf))
+        v = F.linear(n, self.to_v.weight.to(bf))
+        o = ops.EpiAttnFunction.apply(q, k, v, rowp, partner, self.heads, self.F_mat_size)
+        y = F.linear(o, self.to_out[0].weight.to(bf)).float() + self.to_out[0].bias.float()
+        return y / self.rescale_output_factor, None
+
     def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
                 **cross_attention_kwargs):
         if attention_mask is not None or encoder_hidden_states is not None:
             raise _lib.CvdError("EpiSelfAttention builds its own bias / partner rows; attention_mask and "
                                 "encoder_hidden_states must be None (as in every reference call site)")
+        if _wants_grad(self, hidden_states):
+            y, aux = self.attend_train(hidden_states.to(torch.bfloat16), F_mats, H_mats, **cross_attention_kwargs)
+            return y.to(hidden_states.dtype), aux
         y, aux = self.attend(hidden_states, F_mats, H_mats, **cross_attention_kwargs)
         w = self._w
         out = (y.float() + w.f32("bo", self.to_out[0].bias)) / self.rescale_output_factor
@@ -397,9 +451,31 @@ class EpiTransformerBlock(nn.Module):
         hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
         return hs, hb, aux_all
 
+    def forward_train(self, hs, F_mats, H_mats=None, cross_attention_kwargs: Dict[str, Any] = {}):
+        """Differentiable twin of :meth:`forward_stream` (fp32 residual stream, bf16 GEMM operands -- the same
+        precision split as the inference kernels): LayerNorm / GEGLU / residual adds are torch ops recorded by
+        autograd, the attention core is the CUDA forward/backward pair.  epi_module.py:254-268."""
+        bf = torch.bfloat16
+        C = hs.shape[-1]
+        aux_all = []
+        for attn, norm in zip(self.attention_blocks, self.norms):
+            n = F.layer_norm(hs, (C,), norm.weight.float(), norm.bias.float(), norm.eps).to(bf)
+            y, aux = attn.attend_train(n, F_mats=F_mats, H_mats=H_mats, **cross_attention_kwargs)
+            hs = hs + y
+            aux_all.append(aux)
+        n = F.layer_norm(hs, (C,), self.ff_norm.weight.float(), self.ff_norm.bias.float(), self.ff_norm.eps).to(bf)
+        proj, out = self.ff.net[0].proj, self.ff.net[2]
+        hg = F.linear(n, proj.weight.to(bf)).float() + proj.bias.float()
+        hcol, gate = hg.chunk(2, dim=-1)
+        act = (hcol * F.gelu(gate)).to(bf)
+        hs = hs + F.linear(act, out.weight.to(bf)).float() + out.bias.float()
+        return hs, aux_all
+
     def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
                 cross_attention_kwargs: Dict[str, Any] = {}):
-        _require_inference(self, hidden_states)
+        if _wants_grad(self, hidden_states):
+            hs, aux = self.forward_train(hidden_states.float(), F_mats, H_mats, cross_attention_kwargs)
+            return hs.to(hidden_states.dtype), aux
         hs = hidden_states.float().contiguous().clone()
         hs, _, aux = self.forward_stream(hs, F_mats, H_mats, cross_attention_kwargs)
         return hs.to(hidden_states.dtype), aux
@@ -440,7 +516,6 @@ class EpiTransformer3DModel(nn.Module):
     def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
                 cross_attention_kwargs: Dict[str, Any] = {}):
         assert hidden_states.dim() == 5, f"Expected hidden_states to have ndim=5, but got ndim={hidden_states.dim()}."
-        _require_inference(self, hidden_states)
         x = hidden_states.contiguous()
         w = self._w
         if F_mats is not None:   # epi_module.py:166-170
@@ -450,6 +525,8 @@ class EpiTransformer3DModel(nn.Module):
                 F_mats = [F_mats[0].reshape(-1, 3, 3), F_mats[1]]
         if H_mats is not None:
             H_mats = H_mats.reshape(-1, 3, 3)
+        if _wants_grad(self, hidden_states):
+            return self.forward_train(x, F_mats, H_mats, cross_attention_kwargs)
         g = ops.groupnorm_tokens(x, w.f32("gn_w", self.norm.weight), w.f32("gn_b", self.norm.bias), self.norm.num_groups,
                                  self.norm.eps, _lib.LAYOUT_BF_HW)
         # proj_in writes the fp32 residual stream directly (no bf16 round trip, no conversion pass); its bias is owed
@@ -469,6 +546,31 @@ class EpiTransformer3DModel(nn.Module):
         t = F.linear(hb, w.bf16("out_w", self.proj_out.weight))
         out = ops.tokens_to_video(t, w.f32("out_b", self.proj_out.bias), x, _lib.LAYOUT_BF_HW)
         return out, aux_all
+
+
+def _epi_transformer_forward_train(self, x, F_mats, H_mats, cross_attention_kwargs):
+    """Training step through the sync module (BASELINE config 5): same arithmetic as
+    :meth:`EpiTransformer3DModel.forward` -- per-frame GroupNorm (resnet.py:30-40), token layout, proj_in, blocks,
+    proj_out, inverse layout, residual (epi_module.py:157-188) -- with autograd-recorded torch glue around the CUDA
+    attention forward/backward.  No CPU path: the attention core raises without the extension."""
+    if not x.is_cuda:
+        raise _lib.CvdError("cvd_b200 has no CPU path: hidden_states must be a CUDA tensor")
+    bf = torch.bfloat16
+    B, C, Fr, h, w = x.shape
+    xt = x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w)
+    g = F.group_norm(xt.float(), self.norm.num_groups, self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
+    tok = g.permute(0, 2, 3, 1).reshape(B * Fr, h * w, C).to(bf)
+    hs = F.linear(tok, self.proj_in.weight.to(bf)).float() + self.proj_in.bias.float()
+    aux_all = []
+    for block in self.transformer_blocks:
+        hs, aux = block.forward_train(hs, F_mats, H_mats, cross_attention_kwargs)
+        aux_all += aux
+    t = F.linear(hs.to(bf), self.proj_out.weight.to(bf)).float() + self.proj_out.bias.float()
+    out = t.reshape(B, Fr, h, w, C).permute(0, 4, 1, 2, 3) + x.float()
+    return out.to(x.dtype), aux_all
+
+
+EpiTransformer3DModel.forward_train = _epi_transformer_forward_train
 
 
 class EpiModule(nn.Module):
