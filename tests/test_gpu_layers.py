@@ -200,9 +200,14 @@ def test_temporal_module_vs_reference_fixture(golden, dev, case):
     assert_close(y.cpu() - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
 
 
-def test_training_mode_is_refused(dev):
+def test_training_mode_is_refused_by_the_temporal_module(dev):
+    """The motion module is frozen in train_epi_control.py (only the epi parameters train, :270-283) and its kernels are
+    forward-only: asked for a graph, it refuses instead of silently detaching.  (The epi module trains:
+    tests/test_gpu_training.py.)"""
     import cvd_b200
-    m = cvd_b200.EpiModule(320, num_transformer_block=1, attention_block_types=["Epi_Self"]).to(dev).train()
+    m = cvd_b200.VanillaTemporalModule(320, num_attention_heads=8, num_transformer_block=1,
+                                       attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                                       temporal_position_encoding_max_len=32, zero_initialize=False).to(dev).train()
     x = torch.zeros(2, 320, 16, 4, 4, device=dev)
     with pytest.raises(NotImplementedError):
-        m(x, F_mats=torch.zeros(2, 16, 3, 3, device=dev))
+        m(x, cross_attention_kwargs={"pose_feature": None})
