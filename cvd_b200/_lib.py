@@ -28,6 +28,7 @@ SIGNATURES = {
     "cvd_epi_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_simt": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_debug": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "cvd_epi_attn_pp_profile_dump": [],
     "cvd_groupnorm_tokens_fwd": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "cvd_layernorm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cvd_residual_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _F, _P],

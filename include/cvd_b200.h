@@ -90,6 +90,11 @@ int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const f
                            int heads, int head_dim, int n_partners, int feat, float F_mat_size,
                            cvd_stream_t stream);
 
+/* Profiling aid: with CVD_ATTN_PP=1 and CVD_ATTN_PP_PROF=1 in the environment the opt-in ping-pong variant of the
+ * d=40 kernel records per-CTA cycle counters (softmax-side s_full waits, issuer-side waits and issue phases); this
+ * prints their means for the last such launch to stderr.  No effect on results. */
+int cvd_epi_attn_pp_profile_dump(void);
+
 /* ---- f3 (first CUDA path): forward with the statistic the backward needs, and the backward of the attention core.
  *      Replaces autograd through EpiAttnProcessor (attention_processor.py:573-619) in train_epi_control.py:512-642; the
  *      epipolar bias has no gradient (epi_module.py:329,393).

@@ -165,3 +165,19 @@ def test_two_warpgroup_variant_forced(dev):
                           "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_ping_pong_variant_forced(dev):
+    """The d = 40 ping-pong kernel (two query tiles per CTA, every softmax warp alternating between two chains) is an
+    opt-in A/B variant (CVD_ATTN_PP=1, measured slower than the default: profiles/); it must still be exact."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CVD_ATTN_WG2_CHILD") == "1":
+        pytest.skip("already inside a forced-variant child")
+    env = dict(os.environ, CVD_ATTN_PP="1", CVD_ATTN_WG2_CHILD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_attention.py"), "-m", "gpu",
+                          "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
