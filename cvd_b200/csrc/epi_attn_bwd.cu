@@ -18,7 +18,6 @@ namespace cvd {
 namespace bwd {
 
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kDH = 40;       // head-dim slice of dQ / dK / dV per CTA
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -58,6 +57,9 @@ struct CfgB {
   static constexpr int kDP = kD16 + 8;              // pitch of the row-major tiles (elements): 16-byte rows, 4-bank shift
   static constexpr int kTP = BLK + 8;               // pitch of the transposed tiles
   static constexpr int kWarps = BLK / 16;
+  // head-dim slice of dQ / dK / dV per CTA: S and dP are recomputed once per slice, so wide heads take 80-wide slices
+  // (d = 160: 2 instead of 4 recomputations, d = 80: none); the accumulators of an 80-wide slice are 120 registers
+  static constexpr int kDH = D % 80 == 0 ? 80 : 40;
   static constexpr int kChunks = D / kDH;
   static_assert(D % kDH == 0, "head_dim must be a multiple of 40");
   static constexpr size_t kSmem = (size_t)(4 * BLK * kDP + 3 * kDH * kTP + 2 * BLK * kTP) * sizeof(__nv_bfloat16);
@@ -70,6 +72,7 @@ __device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ src,
                                           __nv_bfloat16* dst, __nv_bfloat16* dst_t) {
   using Cf = CfgB<D, BLK>;
   constexpr int kVec = Cf::kD16 / 8;
+  constexpr int kDH = Cf::kDH;
   for (int i = threadIdx.x; i < BLK * kVec; i += Cf::kWarps * 32) {
     const int row = i / kVec, v = i % kVec;
     uint4 t = make_uint4(0u, 0u, 0u, 0u);
@@ -90,6 +93,7 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
                     const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse, const float* __restrict__ delta,
                     float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv, int N, int H, int feat, float step) {
   using Cf = CfgB<D, BLK>;
+  constexpr int kDH = Cf::kDH;
   constexpr int DP = Cf::kDP, TP = Cf::kTP, NT = BLK / 8, KS = Cf::kD16 / 16, OT = kDH / 8;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
