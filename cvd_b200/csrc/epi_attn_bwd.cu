@@ -25,6 +25,10 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// fp32 pair reduction into global memory (REDG.ADD.F32x2): half the reduction requests of two scalar atomics
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ uint32_t packbf(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -224,10 +228,8 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       for (int ot = 0; ot < OT; ++ot) {
         float* d0 = dq + ((size_t)r * N + qrow[0]) * C + (size_t)h * D + c0 + ot * 8 + 2 * t;
         float* d1 = dq + ((size_t)r * N + qrow[1]) * C + (size_t)h * D + c0 + ot * 8 + 2 * t;
-        atomicAdd(d0, dqa[ot][0] * scale);
-        atomicAdd(d0 + 1, dqa[ot][1] * scale);
-        atomicAdd(d1, dqa[ot][2] * scale);
-        atomicAdd(d1 + 1, dqa[ot][3] * scale);
+        red_add2(d0, dqa[ot][0] * scale, dqa[ot][1] * scale);
+        red_add2(d1, dqa[ot][2] * scale, dqa[ot][3] * scale);
       }
     }
     __syncthreads();                             // P^T and dS^T of all warps are in shared memory
@@ -260,14 +262,10 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     float* k1 = dk + (krow0 + 8) * C + col;
     float* v0 = dv + krow0 * C + col;
     float* v1 = dv + (krow0 + 8) * C + col;
-    atomicAdd(k0, dk_acc[ot][0] * scale);
-    atomicAdd(k0 + 1, dk_acc[ot][1] * scale);
-    atomicAdd(k1, dk_acc[ot][2] * scale);
-    atomicAdd(k1 + 1, dk_acc[ot][3] * scale);
-    atomicAdd(v0, dv_acc[ot][0]);
-    atomicAdd(v0 + 1, dv_acc[ot][1]);
-    atomicAdd(v1, dv_acc[ot][2]);
-    atomicAdd(v1 + 1, dv_acc[ot][3]);
+    red_add2(k0, dk_acc[ot][0] * scale, dk_acc[ot][1] * scale);
+    red_add2(k1, dk_acc[ot][2] * scale, dk_acc[ot][3] * scale);
+    red_add2(v0, dv_acc[ot][0], dv_acc[ot][1]);
+    red_add2(v1, dv_acc[ot][2], dv_acc[ot][3]);
   }
 }
 
