@@ -29,6 +29,16 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void red_add2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
+// ldmatrix: four 8x8 bf16 tiles per instruction; lane l supplies the address of row (l & 7) of tile (l >> 3).
+// .trans hands every thread the element pair of the transposed tile.
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], const __nv_bfloat16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ uint32_t packbf(float lo, float hi) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -66,27 +76,19 @@ struct CfgB {
   static constexpr int kDH = D % 80 == 0 ? 80 : 40;
   static constexpr int kChunks = D / kDH;
   static_assert(D % kDH == 0, "head_dim must be a multiple of 40");
-  static constexpr size_t kSmem = (size_t)(4 * BLK * kDP + 3 * kDH * kTP + 2 * BLK * kTP) * sizeof(__nv_bfloat16);
+  static constexpr size_t kSmem = (size_t)(4 * BLK * kDP + 2 * BLK * kTP) * sizeof(__nv_bfloat16);
 };
 
-// rows [row0, row0 + BLK) of a [rows, C] bf16 matrix, columns [h*D, h*D + D) -> dst [BLK][DP] (pad columns zero) and,
-// if dst_t != nullptr, columns [c0, c0 + 40) transposed -> dst_t [40][TP]
+// rows [row0, row0 + BLK) of a [rows, C] bf16 matrix, columns [h*D, h*D + D) -> dst [BLK][DP] (pad columns zero)
 template <int D, int BLK>
-__device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ src, size_t row0, int C, int h, int c0,
-                                          __nv_bfloat16* dst, __nv_bfloat16* dst_t) {
+__device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ src, size_t row0, int C, int h, __nv_bfloat16* dst) {
   using Cf = CfgB<D, BLK>;
   constexpr int kVec = Cf::kD16 / 8;
-  constexpr int kDH = Cf::kDH;
   for (int i = threadIdx.x; i < BLK * kVec; i += Cf::kWarps * 32) {
     const int row = i / kVec, v = i % kVec;
     uint4 t = make_uint4(0u, 0u, 0u, 0u);
     if (v * 8 < D) t = *reinterpret_cast<const uint4*>(src + (row0 + row) * (size_t)C + (size_t)h * D + v * 8);
     *reinterpret_cast<uint4*>(dst + row * Cf::kDP + v * 8) = t;
-    if (dst_t != nullptr && v * 8 >= c0 && v * 8 < c0 + kDH) {
-      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst_t[(v * 8 - c0 + j) * Cf::kTP + row] = e[j];
-    }
   }
 }
 
@@ -104,11 +106,8 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   __nv_bfloat16* sdO = sQ + BLK * DP;
   __nv_bfloat16* sK = sdO + BLK * DP;
   __nv_bfloat16* sV = sK + BLK * DP;
-  __nv_bfloat16* sQt = sV + BLK * DP;          // [40][TP]  Q^T slice
-  __nv_bfloat16* sdOt = sQt + kDH * TP;        // [40][TP]  dO^T slice
-  __nv_bfloat16* sKt = sdOt + kDH * TP;        // [40][TP]  K^T slice
-  __nv_bfloat16* sPt = sKt + kDH * TP;         // [BLK keys][TP]  P^T
-  __nv_bfloat16* sdSt = sPt + BLK * TP;        // [BLK keys][TP]  dS^T
+  __nv_bfloat16* sP = sV + BLK * DP;           // [BLK queries][TP]  P   (row-major; transposed on the way out by ldmatrix.trans)
+  __nv_bfloat16* sdS = sP + BLK * TP;          // [BLK queries][TP]  dS
 
   const int C = H * D;
   const int jb = blockIdx.x / Cf::kChunks, c0 = (blockIdx.x % Cf::kChunks) * kDH;   // key block, head-dim slice
@@ -119,8 +118,9 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const float scale = rsqrtf((float)D), scale2 = scale * kLog2e;
   const float off = (step - 1.0f) * 0.5f;
 
-  load_tile<D, BLK>(k, (size_t)rr * N + (size_t)jb * BLK, C, h, c0, sK, sKt);
-  load_tile<D, BLK>(v, (size_t)rr * N + (size_t)jb * BLK, C, h, c0, sV, nullptr);
+  const int lr = lane & 7, lm = lane >> 3;       // ldmatrix: row and tile this lane addresses
+  load_tile<D, BLK>(k, (size_t)rr * N + (size_t)jb * BLK, C, h, sK);
+  load_tile<D, BLK>(v, (size_t)rr * N + (size_t)jb * BLK, C, h, sV);
 
   // row table of this (r): effective line matrix, band, weight
   float Pm[11];
@@ -138,9 +138,9 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 
   const int nqb = N / BLK;
   for (int ib = 0; ib < nqb; ++ib) {
-    __syncthreads();                             // previous iteration's readers of sQ / sdO / sPt / sdSt are done
-    load_tile<D, BLK>(q, (size_t)r * N + (size_t)ib * BLK, C, h, c0, sQ, sQt);
-    load_tile<D, BLK>(d_o, (size_t)r * N + (size_t)ib * BLK, C, h, c0, sdO, sdOt);
+    __syncthreads();                             // previous iteration's readers of sQ / sdO / sP / sdS are done
+    load_tile<D, BLK>(q, (size_t)r * N + (size_t)ib * BLK, C, h, sQ);
+    load_tile<D, BLK>(d_o, (size_t)r * N + (size_t)ib * BLK, C, h, sdO);
     __syncthreads();
 
     // ---- S = Q K^T and dP = dO V^T for this warp's 16 query rows x BLK keys
@@ -149,20 +149,20 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) s[nt][e] = dp[nt][e] = 0.f;
-    const __nv_bfloat16* qa = sQ + (warp * 16 + g) * DP + 2 * t;
-    const __nv_bfloat16* da = sdO + (warp * 16 + g) * DP + 2 * t;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t a0 = lds32(qa + ks * 16), a1 = lds32(qa + 8 * DP + ks * 16), a2 = lds32(qa + ks * 16 + 8),
-                     a3 = lds32(qa + 8 * DP + ks * 16 + 8);
-      const uint32_t e0 = lds32(da + ks * 16), e1 = lds32(da + 8 * DP + ks * 16), e2 = lds32(da + ks * 16 + 8),
-                     e3 = lds32(da + 8 * DP + ks * 16 + 8);
+      uint32_t aq[4], ad[4];
+      ldsm4(aq, sQ + (warp * 16 + lr + 8 * (lm & 1)) * DP + ks * 16 + 8 * (lm >> 1));
+      ldsm4(ad, sdO + (warp * 16 + lr + 8 * (lm & 1)) * DP + ks * 16 + 8 * (lm >> 1));
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const __nv_bfloat16* kb = sK + (nt * 8 + g) * DP + ks * 16 + 2 * t;
-        const __nv_bfloat16* vb = sV + (nt * 8 + g) * DP + ks * 16 + 2 * t;
-        mma16816(s[nt], a0, a1, a2, a3, lds32(kb), lds32(kb + 8));
-        mma16816(dp[nt], e0, e1, e2, e3, lds32(vb), lds32(vb + 8));
+      for (int nt = 0; nt < NT; nt += 2) {       // two key tiles per ldmatrix.x4
+        uint32_t bk[4], bv[4];
+        ldsm4(bk, sK + ((nt + (lm >> 1)) * 8 + lr) * DP + ks * 16 + 8 * (lm & 1));
+        ldsm4(bv, sV + ((nt + (lm >> 1)) * 8 + lr) * DP + ks * 16 + 8 * (lm & 1));
+        mma16816(s[nt], aq[0], aq[1], aq[2], aq[3], bk[0], bk[1]);
+        mma16816(s[nt + 1], aq[0], aq[1], aq[2], aq[3], bk[2], bk[3]);
+        mma16816(dp[nt], ad[0], ad[1], ad[2], ad[3], bv[0], bv[1]);
+        mma16816(dp[nt + 1], ad[0], ad[1], ad[2], ad[3], bv[2], bv[3]);
       }
     }
 
@@ -186,6 +186,7 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
+      float pv[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int kl = nt * 8 + 2 * t + (e & 1);           // key inside the block
@@ -198,13 +199,16 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
           if (!(fabsf(bias) <= 3.0e38f)) bias = 0.f;       // NaN / inf geometry -> 0 (epi_module.py:404-407)
           x += bias;
         }
-        const float p = ptx::ex2(x);
-        const float ds = p * (dp[nt][e] - dl[i]);
-        s[nt][e] = ds;                                     // s now holds dS (A operand of dQ)
-        const int ql = warp * 16 + g + 8 * i;              // query inside the block
-        sPt[kl * TP + ql] = __float2bfloat16_rn(p);
-        sdSt[kl * TP + ql] = __float2bfloat16_rn(ds);
+        pv[e] = ptx::ex2(x);
+        s[nt][e] = pv[e] * (dp[nt][e] - dl[i]);            // s now holds dS (A operand of dQ)
       }
+      // row-major [query][key], one 32-bit store per key pair (conflict-free: 36-word pitch)
+      __nv_bfloat16* p0 = sP + (warp * 16 + g) * TP + nt * 8 + 2 * t;
+      __nv_bfloat16* d0 = sdS + (warp * 16 + g) * TP + nt * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(p0) = packbf(pv[0], pv[1]);
+      *reinterpret_cast<uint32_t*>(p0 + 8 * TP) = packbf(pv[2], pv[3]);
+      *reinterpret_cast<uint32_t*>(d0) = packbf(s[nt][0], s[nt][1]);
+      *reinterpret_cast<uint32_t*>(d0 + 8 * TP) = packbf(s[nt][2], s[nt][3]);
     }
 
     // ---- dQ[16 x 40] = dS[16 x BLK] K[BLK x 40-slice] / sqrt(d)  -> global (atomic)
@@ -219,9 +223,12 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         const uint32_t a0 = packbf(s[2 * kk][0], s[2 * kk][1]), a1 = packbf(s[2 * kk][2], s[2 * kk][3]),
                        a2 = packbf(s[2 * kk + 1][0], s[2 * kk + 1][1]), a3 = packbf(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
-        for (int ot = 0; ot < OT; ++ot) {
-          const __nv_bfloat16* b = sKt + (ot * 8 + g) * TP + kk * 16 + 2 * t;
-          mma16816(dqa[ot], a0, a1, a2, a3, lds32(b), lds32(b + 8));
+        for (int ot = 0; ot < OT; ot += 2) {     // K[key][d] as the (key x d) B operand: ldmatrix.trans, two d tiles at a time
+          const int o2 = ot + 1 < OT ? ot + (lm >> 1) : ot;
+          uint32_t bk[4];
+          ldsm4t(bk, sK + (kk * 16 + lr + 8 * (lm & 1)) * DP + c0 + o2 * 8);
+          mma16816(dqa[ot], a0, a1, a2, a3, bk[0], bk[1]);
+          if (ot + 1 < OT) mma16816(dqa[ot + 1], a0, a1, a2, a3, bk[2], bk[3]);
         }
       }
 #pragma unroll
@@ -235,20 +242,24 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     __syncthreads();                             // P^T and dS^T of all warps are in shared memory
 
     // ---- dV[16 keys x 40] += P^T[16 x BLK q] dO[BLK q x 40-slice];  dK likewise with dS^T and Q
-    const __nv_bfloat16* pa = sPt + (warp * 16 + g) * TP + 2 * t;
-    const __nv_bfloat16* sa = sdSt + (warp * 16 + g) * TP + 2 * t;
 #pragma unroll
     for (int kk = 0; kk < BLK / 16; ++kk) {
-      const uint32_t a0 = lds32(pa + kk * 16), a1 = lds32(pa + 8 * TP + kk * 16), a2 = lds32(pa + kk * 16 + 8),
-                     a3 = lds32(pa + 8 * TP + kk * 16 + 8);
-      const uint32_t e0 = lds32(sa + kk * 16), e1 = lds32(sa + 8 * TP + kk * 16), e2 = lds32(sa + kk * 16 + 8),
-                     e3 = lds32(sa + 8 * TP + kk * 16 + 8);
+      // A = P^T / dS^T (keys x queries) out of the row-major [query][key] tiles: ldmatrix.trans
+      uint32_t ap[4], as_[4];
+      ldsm4t(ap, sP + (kk * 16 + lr + 8 * (lm >> 1)) * TP + warp * 16 + 8 * (lm & 1));
+      ldsm4t(as_, sdS + (kk * 16 + lr + 8 * (lm >> 1)) * TP + warp * 16 + 8 * (lm & 1));
 #pragma unroll
-      for (int ot = 0; ot < OT; ++ot) {
-        const __nv_bfloat16* bo = sdOt + (ot * 8 + g) * TP + kk * 16 + 2 * t;
-        const __nv_bfloat16* bq = sQt + (ot * 8 + g) * TP + kk * 16 + 2 * t;
-        mma16816(dv_acc[ot], a0, a1, a2, a3, lds32(bo), lds32(bo + 8));
-        mma16816(dk_acc[ot], e0, e1, e2, e3, lds32(bq), lds32(bq + 8));
+      for (int ot = 0; ot < OT; ot += 2) {       // B = dO / Q (queries x d): ldmatrix.trans, two d tiles at a time
+        const int o2 = ot + 1 < OT ? ot + (lm >> 1) : ot;
+        uint32_t bo[4], bq[4];
+        ldsm4t(bo, sdO + (kk * 16 + lr + 8 * (lm & 1)) * DP + c0 + o2 * 8);
+        ldsm4t(bq, sQ + (kk * 16 + lr + 8 * (lm & 1)) * DP + c0 + o2 * 8);
+        mma16816(dv_acc[ot], ap[0], ap[1], ap[2], ap[3], bo[0], bo[1]);
+        mma16816(dk_acc[ot], as_[0], as_[1], as_[2], as_[3], bq[0], bq[1]);
+        if (ot + 1 < OT) {
+          mma16816(dv_acc[ot + 1], ap[0], ap[1], ap[2], ap[3], bo[2], bo[3]);
+          mma16816(dk_acc[ot + 1], as_[0], as_[1], as_[2], as_[3], bq[2], bq[3]);
+        }
       }
     }
   }
