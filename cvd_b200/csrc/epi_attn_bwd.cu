@@ -76,7 +76,10 @@ struct CfgB {
   static constexpr int kDH = D % 80 == 0 ? 80 : 40;
   static constexpr int kChunks = D / kDH;
   static_assert(D % kDH == 0, "head_dim must be a multiple of 40");
-  static constexpr size_t kSmem = (size_t)(4 * BLK * kDP + 2 * BLK * kTP) * sizeof(__nv_bfloat16);
+  // Q / dO tiles double-buffered (cp.async) where two CTAs still fit per SM; d = 160 (N <= 64 in the UNet: one or
+  // four query blocks) keeps one stage and two CTAs per SM instead
+  static constexpr int kQStages = D <= 80 ? 2 : 1;
+  static constexpr size_t kSmem = (size_t)((2 + 2 * kQStages) * BLK * kDP + 2 * BLK * kTP) * sizeof(__nv_bfloat16);
 };
 
 // rows [row0, row0 + BLK) of a [rows, C] bf16 matrix, columns [h*D, h*D + D) -> dst [BLK][DP] (pad columns zero)
@@ -92,6 +95,24 @@ __device__ __forceinline__ void load_tile(const __nv_bfloat16* __restrict__ src,
   }
 }
 
+// same tile through cp.async (16-byte chunks, pad columns zero-filled by a zero source size): the copy of the next query
+// block is in flight while the current one is multiplied
+template <int D, int BLK>
+__device__ __forceinline__ void load_tile_async(const __nv_bfloat16* __restrict__ src, size_t row0, int C, int h, __nv_bfloat16* dst) {
+  using Cf = CfgB<D, BLK>;
+  constexpr int kVec = Cf::kD16 / 8;
+  for (int i = threadIdx.x; i < BLK * kVec; i += Cf::kWarps * 32) {
+    const int row = i / kVec, v = i % kVec;
+    const bool in = v * 8 < D;
+    const __nv_bfloat16* g = src + (row0 + row) * (size_t)C + (size_t)h * D + (in ? v * 8 : 0);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + row * Cf::kDP + v * 8);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(g), "r"(in ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
 template <int D, int BLK>
 __global__ void __launch_bounds__(CfgB<D, BLK>::kWarps * 32)
 epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
@@ -102,9 +123,10 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   constexpr int kDH = Cf::kDH;
   constexpr int DP = Cf::kDP, TP = Cf::kTP, NT = BLK / 8, KS = Cf::kD16 / 16, OT = kDH / 8;
   extern __shared__ __align__(16) unsigned char bwd_smem[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(bwd_smem);
-  __nv_bfloat16* sdO = sQ + BLK * DP;
-  __nv_bfloat16* sK = sdO + BLK * DP;
+  constexpr int QS = Cf::kQStages;
+  __nv_bfloat16* sQ2 = reinterpret_cast<__nv_bfloat16*>(bwd_smem);   // [stages][BLK][DP]
+  __nv_bfloat16* sdO2 = sQ2 + QS * BLK * DP;                         // [stages][BLK][DP]
+  __nv_bfloat16* sK = sdO2 + QS * BLK * DP;
   __nv_bfloat16* sV = sK + BLK * DP;
   __nv_bfloat16* sP = sV + BLK * DP;           // [BLK queries][TP]  P   (row-major; transposed on the way out by ldmatrix.trans)
   __nv_bfloat16* sdS = sP + BLK * TP;          // [BLK queries][TP]  dS
@@ -137,10 +159,27 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     for (int e = 0; e < 4; ++e) dk_acc[i][e] = dv_acc[i][e] = 0.f;
 
   const int nqb = N / BLK;
+  if (QS == 2) {
+    load_tile_async<D, BLK>(q, (size_t)r * N, C, h, sQ2);
+    load_tile_async<D, BLK>(d_o, (size_t)r * N, C, h, sdO2);
+    cp_async_commit();
+  }
   for (int ib = 0; ib < nqb; ++ib) {
-    __syncthreads();                             // previous iteration's readers of sQ / sdO / sP / sdS are done
-    load_tile<D, BLK>(q, (size_t)r * N + (size_t)ib * BLK, C, h, sQ);
-    load_tile<D, BLK>(d_o, (size_t)r * N + (size_t)ib * BLK, C, h, sdO);
+    __syncthreads();                             // previous iteration's readers of the other stage / sP / sdS are done
+    const int stg = QS == 2 ? (ib & 1) : 0;
+    const __nv_bfloat16* sQ = sQ2 + stg * BLK * DP;
+    const __nv_bfloat16* sdO = sdO2 + stg * BLK * DP;
+    if (QS == 1) {
+      load_tile<D, BLK>(q, (size_t)r * N + (size_t)ib * BLK, C, h, sQ2);
+      load_tile<D, BLK>(d_o, (size_t)r * N + (size_t)ib * BLK, C, h, sdO2);
+    } else if (ib + 1 < nqb) {                   // next query block: in flight under this block's MMAs
+      load_tile_async<D, BLK>(q, (size_t)r * N + (size_t)(ib + 1) * BLK, C, h, sQ2 + ((ib + 1) & 1) * BLK * DP);
+      load_tile_async<D, BLK>(d_o, (size_t)r * N + (size_t)(ib + 1) * BLK, C, h, sdO2 + ((ib + 1) & 1) * BLK * DP);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     // ---- S = Q K^T and dP = dO V^T for this warp's 16 query rows x BLK keys
