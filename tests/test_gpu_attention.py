@@ -167,15 +167,18 @@ def test_two_warpgroup_variant_forced(dev):
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
 
 
-def test_ping_pong_variant_forced(dev):
-    """The d = 40 ping-pong kernel (two query tiles per CTA, every softmax warp alternating between two chains) is an
-    opt-in A/B variant (CVD_ATTN_PP=1, measured slower than the default: profiles/); it must still be exact."""
+@pytest.mark.parametrize("switch", ["CVD_ATTN_PP", "CVD_ATTN_CS"])
+def test_opt_in_variants_forced(dev, switch):
+    """The d = 40 ping-pong kernel (two query tiles per CTA, every softmax warp alternating between two chains) and the
+    column-split kernel (two warpgroups share each score tile, reference maximum agreed through shared memory) are
+    opt-in A/B variants (measured slower than the default: profiles/); they must still be exact."""
     import os
     import subprocess
     import sys
     if os.environ.get("CVD_ATTN_WG2_CHILD") == "1":
         pytest.skip("already inside a forced-variant child")
-    env = dict(os.environ, CVD_ATTN_PP="1", CVD_ATTN_WG2_CHILD="1")
+    env = dict(os.environ, CVD_ATTN_WG2_CHILD="1")
+    env[switch] = "1"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_attention.py"), "-m", "gpu",
                           "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
