@@ -365,8 +365,10 @@ class EpiSelfAttention(nn.Module):
             rowp = self.pos_encoder.row_params(n, Fm)
             if rowp.shape[0] != R:
                 raise NotImplementedError("the backward kernel takes one partner per row (2-view pairs, BASELINE config 5)")
+        chunked = False
         if self.reference_chunk_quirk and rowp is not None and (R > 200 or N > 2048):
             # epi_module.py:424-451 (see attend): tensor F_mats -> every row attends to ITSELF; list -> hidden[kv_index]
+            chunked = True
             chunk = 128 * 1024 // max(1024, N)
             if (R // chunk) * chunk != R:
                 raise RuntimeError("the reference's chunk branch dropped rows; the residual add cannot broadcast "
@@ -383,7 +385,9 @@ class EpiSelfAttention(nn.Module):
         v = F.linear(n, self.to_v.weight.to(bf))
         o = ops.EpiAttnFunction.apply(q, k, v, rowp, partner, self.heads, self.F_mat_size)
         y = F.linear(o, self.to_out[0].weight.to(bf)).float() + self.to_out[0].bias.float()
-        return y / self.rescale_output_factor, None
+        # aux = {"query", "key"} (attention_processor.py:595-596,650; graph tensors: train_epi_control.py:607 may put a
+        # loss on them); None in the memory-relief branch like the reference (epi_module.py:450)
+        return y / self.rescale_output_factor, (None if chunked else _Aux(q, k, partner))
 
     def forward(self, hidden_states, F_mats=None, H_mats=None, encoder_hidden_states=None, attention_mask=None,
                 **cross_attention_kwargs):

@@ -52,6 +52,7 @@ def test_epi_module_train_step_vs_oracle_autograd(golden, dev, C, feat, B):
     y, aux = m(xp, F_mats=Fm.to(dev), temb=None, encoder_hidden_states=None, cross_attention_kwargs={"pose_feature": None})
     (y * wgt.to(dev)).sum().backward()
     assert y.shape == x.shape and y.dtype == x.dtype and len(aux) == 2
+    assert aux[0]["query"].requires_grad and aux[0]["key"].shape == (B * 16, feat * feat, C)
 
     e_fwd = rel_l2((y.detach().cpu() - x), (y_ref.detach() - x))
     e_x = rel_l2(xp.grad.cpu(), x_ref.grad)
