@@ -44,7 +44,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
-EXCHANGE = "NVLink copy engines, 2 row chunks under the attention"
+EXCHANGE = "NVLink copy engines, 2 row chunks under the attention; grids <= 8x8 read the peer's K/V^T in-kernel (TMA over NVLink)"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -338,6 +338,7 @@ def run_ours(args):
                     a = i
             return rr
 
+        partner_local = (partner % R).to(torch.int32)      # row inside the source rank's buffer
         runs = [runs_of(lo, hi) for lo, hi in chunks]
         runs_q = [runs_of(lo, hi) for lo, hi in quarters]
         runs_whole = runs_of(0, R)
@@ -355,6 +356,14 @@ def run_ours(args):
                     # one cross-rank barrier, then the partner rows cross NVLink on the COPY ENGINES in two row chunks on a
                     # side stream; the attention of chunk 0 runs under the transfer of chunk 1 (no SMs are spent on the pull)
                     xk[1].barrier()
+                    if feat * feat <= 128 and len({rk for (_, _, rk, _) in runs_whole}) == 1:
+                        # one query tile per (row, head): the kernel reads the partner's K / V^T tiles straight out of
+                        # the peer's HBM (TMA over NVLink) -- every byte crosses once, no landing buffer, no copy launch.
+                        # (At larger grids the 2..8 query-tile CTAs of a (row, head) would each stream the partner rows
+                        # over the links; those shapes keep the copy-engine exchange below.)
+                        src = runs_whole[0][2]
+                        ops.epi_attn_fwd(q, xk[2][src], xv[2][src], rowp, partner_local, HEADS, F_MAT_SIZE)
+                        continue
                     ev_b.record(main_stream)
                     with torch.cuda.stream(side_stream):
                         side_stream.wait_event(ev_b)
