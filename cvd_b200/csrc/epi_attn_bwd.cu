@@ -226,19 +226,23 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       float pv[4];
+      // this thread's two keys of the tile, key0 and key0 + 1, sit in one key-grid row (feat is even): their grid
+      // coordinates once per tile, not per element (the per-element integer division was most of the instruction stream)
+      const int key0 = jb * BLK + nt * 8 + 2 * t;
+      const float colf = (float)(key0 % feat), rowf = (float)(key0 / feat);
+      float tt0[2], tt1[2];                              // line distance terms of rows g / g + 8 at key0 / key0 + 1
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        tt0[i] = fmaf(As[i], colf, fmaf(Bs[i], rowf, base[i]));
+        tt1[i] = tt0[i] + As[i];
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int kl = nt * 8 + 2 * t + (e & 1);           // key inside the block
-        const int key = jb * BLK + kl;
         const int i = e >> 1;
-        float x = fmaf(s[nt][e], scale2, -l2[i]);
-        if (rowp != nullptr) {
-          const float tt = fmaf(As[i], (float)(key % feat), fmaf(Bs[i], (float)(key / feat), base[i]));
-          float bias = fminf(bandp - fabsf(tt), 0.f);
-          if (!(fabsf(bias) <= 3.0e38f)) bias = 0.f;       // NaN / inf geometry -> 0 (epi_module.py:404-407)
-          x += bias;
-        }
-        pv[e] = ptx::ex2(x);
+        // a non-finite row carries an all-zero table (cvd_epi_row_params, epi_module.py:404-407): bias = 0 without a
+        // per-element check, as in the forward kernels
+        const float bias = rowp != nullptr ? fminf(bandp - fabsf((e & 1) ? tt1[i] : tt0[i]), 0.f) : 0.f;
+        pv[e] = ptx::ex2(fmaf(s[nt][e], scale2, bias - l2[i]));
         s[nt][e] = pv[e] * (dp[nt][e] - dl[i]);            // s now holds dS (A operand of dQ)
       }
       // row-major [query][key], one 32-bit store per key pair (conflict-free: 36-word pitch)
