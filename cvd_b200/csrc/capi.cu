@@ -1,4 +1,6 @@
 // Error reporting and versioning of the C ABI (include/cvd_b200.h).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace cvd {
@@ -14,6 +16,15 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(error_buffer(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVD_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace cvd

@@ -76,4 +76,28 @@ __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p
 template <>
 __device__ __forceinline__ void store_from_float<__half>(__half* p, size_t i, float v) { p[i] = __float2half_rn(v); }
 
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the attribute may begin while its predecessor in
+// the stream is still running -- its CTAs take the slots the predecessor's tail leaves idle, run their prologue, and
+// block in pdl_wait() until the predecessor has completed and its memory is visible.  Every kernel launched that way calls
+// pdl_wait() before its first global-memory access; pdl_trigger() at the top of a kernel lets ITS successor start early.
+// CVD_PDL=0 disables the attribute (plain stream order).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace cvd

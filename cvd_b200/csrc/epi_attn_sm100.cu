@@ -108,6 +108,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int h = (blockIdx.x / kQTiles) % H;
   const int r = blockIdx.x / (kQTiles * H);
   const int total = n_partners * C::kTiles;
+  pdl_trigger();      // the next kernel of the stream may fill the slots this grid's tail leaves idle
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQ);
@@ -138,6 +139,9 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const uint32_t tmemP = C::kSplitP ? bars->tmem_p : tmem + C::kColP;
+  // launched with programmatic stream serialization: the prologue above ran under the tail of the kernel in front (the
+  // row-table prepass, and through it the previous attention call); nothing of global memory has been touched yet
+  pdl_wait();
 
   if (warp == 4) {
     // ===================== TMA producer + MMA issuer (one warp) =====================
@@ -915,8 +919,8 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
-  kern<<<(unsigned)grid, kThreads, C::kSmemBytes, st>>>(tmQ, tmK, tmV, rowp, partner, (__nv_bfloat16*)out, R, H, n_partners,
-                                                        S / (float)FEAT, dbg, lse);
+  CVD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)C::kSmemBytes, st, tmQ, tmK, tmV, rowp, partner,
+                      (__nv_bfloat16*)out, R, H, n_partners, S / (float)FEAT, dbg, lse));
   CVD_LAUNCH_CHECK("epi_attn_fwd_kernel");
   return CVD_OK;
 }

@@ -49,6 +49,8 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
   constexpr int kDT = D / 8;                       // 8-wide output tiles
   static_assert(N % 16 == 0 && N <= 64 && D % 8 == 0, "small-grid kernel: N in {16, 64}");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_trigger();      // programmatic dependent launch (common.cuh): the successor may start under this grid's tail,
+  pdl_wait();         // and this grid was allowed to start under its predecessor's
   const long long task = (long long)blockIdx.x * kWarps + warp;
   if (task >= (long long)R * H * kMBlocks) return;
   const int mb = (int)(task % kMBlocks), h = (int)((task / kMBlocks) % H), r = (int)(task / ((long long)kMBlocks * H));
@@ -188,13 +190,11 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   CVD_REQUIRE(n_partners == 1 || n_partners == 2, "cvd_epi_attn_fwd: %d partners at feat=%d (1 or 2 are instantiated)", n_partners, FEAT);
   const float step = S / (float)FEAT;
   if (n_partners == 1)
-    epi_attn_small_kernel<D, FEAT, 1><<<(unsigned)grid, kWarps * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                                                              (const __nv_bfloat16*)vt, rowp, partner,
-                                                                              (__nv_bfloat16*)out, lse, R, H, step);
+    CVD_CUDA(launch_pdl(epi_attn_small_kernel<D, FEAT, 1>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, (const __nv_bfloat16*)q,
+                        (const __nv_bfloat16*)k, (const __nv_bfloat16*)vt, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
   else
-    epi_attn_small_kernel<D, FEAT, 2><<<(unsigned)grid, kWarps * 32, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                                                              (const __nv_bfloat16*)vt, rowp, partner,
-                                                                              (__nv_bfloat16*)out, lse, R, H, step);
+    CVD_CUDA(launch_pdl(epi_attn_small_kernel<D, FEAT, 2>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, (const __nv_bfloat16*)q,
+                        (const __nv_bfloat16*)k, (const __nv_bfloat16*)vt, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
   CVD_LAUNCH_CHECK("epi_attn_small_kernel");
   return CVD_OK;
 }

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(128) epi_row_params_kernel(const float* __rest
   __shared__ float M[9];
   __shared__ float red[4];
   __shared__ int bad[4];
+  pdl_trigger();      // the attention kernel behind this one may take free slots and run its prologue
+  pdl_wait();         // F_mats / theta may come from the kernel in front; rowp may still be read by it
   if (threadIdx.x < 9) {
     float v = F_mats[(size_t)r * 9 + threadIdx.x];
     if (first_frame_rule != CVD_FF_NONE && (r % frames_per_video) == 0) {
@@ -114,9 +116,8 @@ extern "C" int cvd_epi_row_params(const float* F_mats, const float* theta, float
               "cvd_epi_row_params: unknown first_frame_rule %d", first_frame_rule);
   CVD_REQUIRE(first_frame_rule != CVD_FF_RANDOM_SLOPE || theta, "cvd_epi_row_params: theta required");
   CVD_REQUIRE(frames_per_video > 0, "cvd_epi_row_params: frames_per_video must be positive");
-  cvd::epi_row_params_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(F_mats, theta, rowp, feat, F_mat_size,
-                                                                     pixel_band, decay_alpha, first_frame_rule,
-                                                                     frames_per_video);
+  CVD_CUDA(cvd::launch_pdl(cvd::epi_row_params_kernel, dim3(rows), dim3(128), 0, (cudaStream_t)stream, F_mats, theta, rowp,
+                           feat, F_mat_size, pixel_band, decay_alpha, first_frame_rule, frames_per_video));
   CVD_LAUNCH_CHECK("epi_row_params_kernel");
   return CVD_OK;
 }
