@@ -13,15 +13,17 @@
 //    64 keys per round): Q/K/V^T tiles arrive by TMA (128B swizzle) into shared memory, S, P and
 //    O live in TMEM, P is the TMEM A operand of the second MMA (never through shared memory),
 //    and the softmax denominator is a column of O (V^T carries a row of ones).
-//  * Measured on B200 (profiles/): the MUFU/FMA/ALU work of the softmax is NOT the limiter at
-//    d=40 -- the hand-offs are: every tcgen05.mma / tcgen05.commit costs the issuing warp ~100
-//    cycles and every mbarrier / TMEM round trip 100-350 cycles.  Hence: few, 64-key MMA rounds;
-//    P in its own TMEM columns so Q K^T of tile j+1 is issued as soon as S_j has been read,
-//    overlapping the softmax of tile j; 32 scores in registers at a time (<= 113 registers) so
-//    THREE CTAs are resident per SM at d=40 (TMEM 128 + 32 columns each) and cover each other's
-//    latencies.
-//  * Warp roles per CTA (192 threads): warps 0-3 softmax (one TMEM lane quarter each),
-//    warp 4 TMA producer, warp 5 MMA issuer + TMEM owner (one elected lane issues).
+//  * Measured on B200 (profiles/r01_summary.md): at d=40 the kernel sits between the hand-off latencies (every mbarrier /
+//    TMEM round trip costs 100-350 cycles, a tcgen05.mma / commit 50-100 cycles of the issuing warp) and the softmax
+//    instruction stream (11-12 scheduler cycles per warp-column in the kernel, MUFU floor 8).  Hence: few, 64-key MMA
+//    rounds; P in its own TMEM columns so Q K^T of tile j+1 is issued as soon as S_j has been read, overlapping the
+//    softmax of tile j; THREE CTAs resident per SM at d=40 (TMEM 128 + 32 columns each) covering each other's latencies.
+//  * Warp roles per CTA (160 threads): warps 0-3 softmax (one TMEM lane quarter each), warp 4 TMA producer + MMA issuer +
+//    TMEM owner (one elected lane issues).  Five warps, not six: 3 CTAs are then 15 warps per SM, 4 per scheduler at most,
+//    which leaves 128 registers per thread for the fused softmax loop (18 warps: 96, and it spilled).
+//  * Softmax loop: a tile is walked in four 16-key quarters; in each, every score goes bias -> FFMA2 -> MUFU.EX2 -> F2FP
+//    in one straight-line block (ptxas interleaves the MUFU stream with the FADD2 / FMNMX3 stream only through such true
+//    dependencies), and the reference-maximum vote follows the exponentials.
 //  * Online softmax with a lazily updated reference maximum anchored at the largest score the
 //    row can still reach through the bias: scores are evaluated directly against the reference
 //    (the subtraction is folded into the bias terms) and O is rescaled only when a score
