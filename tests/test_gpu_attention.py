@@ -109,6 +109,18 @@ def test_tcgen05_large_logits_rescale(golden, dev):
     assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=2e-2, what="sharp")
 
 
+@pytest.mark.parametrize("feat,d", [(32, 40), (16, 80), (8, 160)])
+def test_tcgen05_extreme_logits_do_not_overflow(golden, dev, feat, d):
+    """|logit| in the hundreds (2^x overflows fp32 beyond x = 128): the exponentials of a quarter are computed BEFORE the
+    reference-maximum vote, so a quarter whose scores jump far above the reference yields inf speculatively -- the vote
+    must then recompute it against the new reference, and nothing non-finite may survive."""
+    from cvd_b200 import ops
+    q, k, v, vt, rowp, bias, partner = make_case(dev, 32, feat, 8, d, 61, golden, qk_gain=14.0)
+    out = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
+    assert torch.isfinite(out.float()).all()
+    assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=3e-2, max_abs=0.5, what="extreme logits")
+
+
 def test_tcgen05_no_bias_matches_sdpa(golden, dev):
     """rowp = NULL (epi_no_attention_mask): plain cross attention == torch SDPA."""
     from cvd_b200 import ops
