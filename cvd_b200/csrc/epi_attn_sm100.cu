@@ -145,7 +145,36 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // row-table prepass, and through it the previous attention call); nothing of global memory has been touched yet
   pdl_wait();
 
-  if (warp == 4) {
+#ifdef CVD_WHATIF_NOSYNC
+  // profiling build (make EXTRA=-DCVD_WHATIF_NOSYNC, results invalid): the softmax warps run their loop -- TMEM loads,
+  // arithmetic, TMEM stores -- with every hand-off removed and no MMA / TMA issued: the cost of the softmax stream alone
+  // in the production register / occupancy context
+  constexpr bool kNoSync = true;
+#else
+  constexpr bool kNoSync = false;
+#endif
+  if (warp == 4 && kNoSync) {
+    // one real Q K_0^T so that S holds scores (re-read by every "tile"); nothing else is issued
+    if (elect_one()) {
+      mbar_expect_tx(smem_u32(&bars->q_full), C::kQBytes + C::kKBytes);
+#pragma unroll
+      for (int kb = 0; kb < C::kKBlocks; ++kb) {
+        tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
+        tma_load_3d(sK + kb * kTileN * 128, &tmK, kb * 64, h, partner[r] * N, smem_u32(&bars->q_full));
+      }
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&bars->q_full), 0);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int ks = 0; ks < C::kKSteps; ++ks)
+        umma_ss(tmem + C::kColS, umma_desc_k_sw128(sQ + (ks >> 2) * kBlockM * 128 + (ks & 3) * 32),
+                umma_desc_k_sw128(sK + (ks >> 2) * kTileN * 128 + (ks & 3) * 32), kIdescQK, ks > 0);
+      umma_commit(smem_u32(&bars->s_full));
+    }
+    __syncwarp();
+  } else if (warp == 4) {
     // ===================== TMA producer + MMA issuer (one warp) =====================
     // Five warps per CTA: 3 CTAs = 15 warps per SM leave 128 registers per thread (18 warps: 96).  The whole warp walks
     // the loop (waits are warp-wide), one elected lane issues.  Ring stages are refilled by the issuer itself right
@@ -290,7 +319,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (DBG && tid == 0 && j < 32)
         stamps = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kTileN) + ((size_t)blockIdx.x * 32 + j) * 8;
       if (DBG && stamps) stamps[0] = clock64();
-      mbar_wait(smem_u32(&bars->s_full), j & 1);
+      if (!kNoSync || j == 0) mbar_wait(smem_u32(&bars->s_full), j & 1);
       tc_fence_after();
       if (DBG && stamps) stamps[1] = clock64();
 
@@ -345,7 +374,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (q == 0) {
             tmem_ld_wait_dep32(s1);
-            if (!C::kAliasP) {                  // S_j is in registers: the tensor core may start Q K_{j+1}^T
+            if (!C::kAliasP && !kNoSync) {      // S_j is in registers: the tensor core may start Q K_{j+1}^T
               tc_fence_before();
               mbar_arrive(smem_u32(&bars->s_free));
             }
@@ -362,7 +391,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (!first) {
               const float f = need ? ex2(-xmax) : 1.0f;
               if (j > 0) {
-                mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
+                if (!kNoSync) mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int c0 = 0; c0 < C::kDV; c0 += 16) {
@@ -477,7 +506,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (DBG && stamps) stamps[2 + hh] = clock64() + (long long)(preg[hh * 16] & 1u);
       }
       }
-      if (j > 0) {   // the P columns are free once PV(j-1) has read them (aliased mode: implied by s_full(j))
+      if (j > 0 && !kNoSync) {   // the P columns are free once PV(j-1) has read them (aliased mode: implied by s_full(j))
         mbar_wait(smem_u32(&bars->pv_done), (j - 1) & 1);
         tc_fence_after();
       }
@@ -485,12 +514,12 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_st_x32(tP, preg);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full));
+      if (!kNoSync) mbar_arrive(smem_u32(&bars->p_full));
       if (DBG && stamps) stamps[5] = clock64();
     }
 
     // epilogue: O[:, 0:D] / O[:, D]  ->  out[r, n, h*D : (h+1)*D]
-    mbar_wait(smem_u32(&bars->o_done), 0);   // committed once, after the last PV
+    if (!kNoSync) mbar_wait(smem_u32(&bars->o_done), 0);   // committed once, after the last PV
     tc_fence_after();
     uint32_t lraw;
     tmem_ld_x1(tO + D, lraw);
