@@ -251,7 +251,31 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
             torch.cuda.synchronize()
             ms_eager = e2.elapsed_time(e3) / steps
     assert torch.isfinite(out).all()
-    return e0.elapsed_time(e1) / steps, V, ms_eager
+    by_views = None
+    if world == 1:
+        # BASELINE metric "denoise steps/s at 2/4/6 views": the V-view loop (fresh pairing, device F recompute and kv_index
+        # gather per UNet call) with all V views on this one GPU (R = 32 V rows), eager launches, multistep = 1
+        by_views = {"2": {"steps_per_s": 1e3 / (e0.elapsed_time(e1) / steps), "rows": 64, "launch": "one CUDA graph per UNet forward"}}
+        for Vn, rig in ((4, "circle"), (6, "upper_hemi")):
+            lat_v = torch.randn(Vn, 4, 16, 32, 32, device=dev, generator=g)
+            poses_v = [torch.randn(Vn, c, 16, 32 >> i, 32 >> i, device=dev, generator=g) for i, c in enumerate(sync_unet.CHANNELS)]
+            text_v = torch.randn(2, 77, 768, device=dev, generator=g).repeat(Vn, 1, 1)
+            c2w, K = sampler.multiview_cameras(Vn, 16, rig, 0.5, 256)
+
+            def run_v(n):
+                return sampler.sample_multiview(net, lat_v, text_v, sch, n, 8.5, aux_c2w=c2w, aux_K_mats=K,
+                                                pose_embedding_features=poses_v)
+            with torch.no_grad():
+                run_v(2)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                o = run_v(steps)
+                b.record()
+                torch.cuda.synchronize()
+            assert torch.isfinite(o).all()
+            by_views[str(Vn)] = {"steps_per_s": 1e3 / (a.elapsed_time(b) / steps), "rows": 32 * Vn, "launch": "eager", "rig": rig}
+    return e0.elapsed_time(e1) / steps, V, ms_eager, by_views
 
 
 # ------------------------------------------------------------------------------------------
@@ -481,7 +505,7 @@ def run_ours(args):
     # release the kernel-bench buffers before the UNet-level measurement
     del bufs, land, layers, hosts, dev_in
     torch.cuda.empty_cache()
-    ms_denoise, views, ms_eager = (None, 0, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
+    ms_denoise, views, ms_eager, by_views = (None, 0, None, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
 
     # max over ranks
     if world > 1:
@@ -521,6 +545,8 @@ def run_ours(args):
                                "unet": "hot-path skeleton cvd_b200.sync_unet.SyncPathUNet (20 temporal + 20 epi modules at "
                                        "256x256; SD-1.5 spatial blocks excluded -- not comparable to a full-UNet number)",
                                "loop": "sampler.sample_pair" if world == 1 else "sampler.sample_multiview (view-sharded)"}
+            if by_views is not None:
+                line["denoise"]["by_views"] = by_views
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
