@@ -132,7 +132,7 @@ def cfg_pair_index(offset_rows, n_frames=FRAMES):
 
 def sample_multiview(unet, latents, text_embeddings, schedule, num_inference_steps=25, guidance_scale=8.5,
                      aux_c2w=None, aux_K_mats=None, F_mats=None, pose_embedding_features=None, multistep=1,
-                     accumulate_step=1, shard=None, rng=np.random, noise_fn=None, callback=None):
+                     accumulate_step=1, shard=None, rng=np.random, noise_fn=None, callback=None, kv_on_device=False):
     """pipeline_animation_epi_advanced.py:596-705.
 
     latents [V_local,c,f,h,w]; text_embeddings [2*V_local,l,c] already CFG-interleaved per view
@@ -142,6 +142,9 @@ def sample_multiview(unet, latents, text_embeddings, schedule, num_inference_ste
     [V_local,C,f,h,w] (CameraCtrl features), required like in the reference for the sync path to
     be active (``:619``).  ``shard``: :class:`cvd_b200.sharding.ViewShard` or None.  ``noise_fn(shape)``: source of the
     re-noise tensor (default: ``torch.randn`` on the global generator of the latents' device, like ``:701``).
+    ``kv_on_device``: hand kv_index to the UNet as a device int32 tensor instead of the reference's numpy array, so that
+    a CUDA-graphed UNet (:class:`cvd_b200.GraphedModule`) replays ONE graph for every pairing (a numpy kv_index is part
+    of the captured control flow: one graph per distinct pairing).
     """
     from . import ops
     cfg = guidance_scale > 1.0
@@ -184,6 +187,8 @@ def sample_multiview(unet, latents, text_embeddings, schedule, num_inference_ste
                         kv = video_id
                     if shard is not None:
                         kv = shard.local_kv_index(kv, kv.shape[0])
+                    if kv_on_device:
+                        kv = torch.from_numpy(np.ascontiguousarray(kv).astype(np.int32)).to(dev, non_blocking=True)
                     F_in = [Fm, kv] if (V != 2 or shard is not None) else Fm
                 x_in = latents.repeat_interleave(2, dim=0) if cfg else latents
                 x_in = schedule.scale_model_input(x_in, t)

@@ -171,6 +171,36 @@ def test_graphed_unet_equals_eager(dev):
     assert len(gnet._graphs) == 1
 
 
+def test_graphed_multiview_loop_equals_eager(dev):
+    """The V-view loop on a CUDA-graphed UNet with kv_index handed over as a device tensor (one graph for every pairing)
+    gives the same latents as the eager loop with the reference's numpy kv_index (same pairing / re-noise draws)."""
+    import cvd_b200
+    from cvd_b200 import sampler
+    prod, _ = build_pair(dev, levels=2, seed=23)
+    V = 4
+    g = torch.Generator(device=dev).manual_seed(3)
+    lat = torch.randn(V, 4, 16, 8, 8, device=dev, generator=g)
+    text = torch.randn(2, 77, 768, device=dev, generator=g).repeat(V, 1, 1)
+    poses = [torch.randn(V, c, 16, 8 >> i, 8 >> i, device=dev, generator=g) for i, c in enumerate((320, 640))]
+    c2w, K = sampler.multiview_cameras(V, 16, "circle", 0.5, 256)
+    sch = sampler.DDIMSchedule(device=dev)
+    gnet = cvd_b200.GraphedModule(prod)
+
+    def graphed(x, t, **kw):
+        return gnet(x, torch.full((), float(t), device=dev), **kw)
+
+    outs = []
+    for unet, on_dev in ((prod, False), (graphed, True)):
+        np.random.seed(11)
+        torch.manual_seed(11)
+        with torch.no_grad():
+            outs.append(sampler.sample_multiview(unet, lat, text, sch, 3, 4.0, aux_c2w=c2w, aux_K_mats=K,
+                                                 pose_embedding_features=poses, multistep=2, kv_on_device=on_dev).clone())
+    assert torch.isfinite(outs[0]).all()
+    assert float((outs[0] - outs[1]).abs().max()) < 1e-5, float((outs[0] - outs[1]).abs().max())
+    assert len(gnet._graphs) == 1          # five UNet calls, five pairings, one graph
+
+
 def test_pair_ddim_latents_vs_oracle(dev):
     """Two-video loop (pipeline_animation_epi.py), real pose-pair geometry, swap-halves partner."""
     from cvd_b200 import sampler
