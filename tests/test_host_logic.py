@@ -99,3 +99,18 @@ def test_geometry_matches_reference_fixture(golden):
     np.testing.assert_allclose(G.pairwise_fundamental_matrices(c2w, K, pairing).numpy(),
                                O.pairwise_F_mats(c2w, K, pairing).numpy(), rtol=1e-5, atol=1e-9)
     assert np.allclose(G.calc_cross_product_matrix(np.array([1.0, 2.0, 3.0])), O.cross_product_matrix([1, 2, 3]))
+
+
+def test_training_path_has_no_cpu_fallback_either():
+    """train() mode routes EpiModule through the differentiable path; like the inference
+    path it refuses CPU tensors instead of falling back to torch, and the (frozen) temporal module refuses to build a
+    graph at all."""
+    import cvd_b200
+    m = cvd_b200.EpiModule(320, num_attention_heads=8, num_transformer_block=1, attention_block_types=["Epi_Self"]).train()
+    with pytest.raises(cvd_b200.CvdError):
+        m(torch.zeros(2, 320, 16, 4, 4), F_mats=torch.zeros(2, 16, 3, 3))
+    t = cvd_b200.VanillaTemporalModule(320, num_attention_heads=8, num_transformer_block=1,
+                                       attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                                       temporal_position_encoding_max_len=32, zero_initialize=False).train()
+    with pytest.raises((NotImplementedError, cvd_b200.CvdError)):
+        t(torch.zeros(2, 320, 16, 4, 4), cross_attention_kwargs={"pose_feature": None})
