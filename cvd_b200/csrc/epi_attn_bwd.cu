@@ -236,14 +236,20 @@ epi_attn_bwd_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         tt0[i] = fmaf(As[i], colf, fmaf(Bs[i], rowf, base[i]));
         tt1[i] = tt0[i] + As[i];
       }
+      // a non-finite row carries an all-zero table (cvd_epi_row_params, epi_module.py:404-407): bias = 0 without a
+      // per-element check, as in the forward kernels.  The two keys of a thread are one packed fp32x2 lane pair:
+      //   x = S * scale2 + min(band' - l - |t|, -l),   P = 2^x,   dS = P * (dP - delta)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = e >> 1;
-        // a non-finite row carries an all-zero table (cvd_epi_row_params, epi_module.py:404-407): bias = 0 without a
-        // per-element check, as in the forward kernels
-        const float bias = rowp != nullptr ? fminf(bandp - fabsf((e & 1) ? tt1[i] : tt0[i]), 0.f) : 0.f;
-        pv[e] = ptx::ex2(fmaf(s[nt][e], scale2, bias - l2[i]));
-        s[nt][e] = pv[e] * (dp[nt][e] - dl[i]);            // s now holds dS (A operand of dQ)
+      for (int i = 0; i < 2; ++i) {
+        const float bm = bandp - l2[i], nl = -l2[i];
+        const float v0 = rowp != nullptr ? fminf(bm - fabsf(tt0[i]), nl) : nl;
+        const float v1 = rowp != nullptr ? fminf(bm - fabsf(tt1[i]), nl) : nl;
+        float x0, x1;
+        ptx::unpack2(ptx::fma2(ptx::pack2(s[nt][2 * i], s[nt][2 * i + 1]), ptx::pack2(scale2, scale2), ptx::pack2(v0, v1)), x0, x1);
+        pv[2 * i] = ptx::ex2(x0);
+        pv[2 * i + 1] = ptx::ex2(x1);
+        const uint64_t dd = ptx::add2(ptx::pack2(dp[nt][2 * i], dp[nt][2 * i + 1]), ptx::pack2(-dl[i], -dl[i]));
+        ptx::unpack2(ptx::fma2(ptx::pack2(pv[2 * i], pv[2 * i + 1]), dd, ptx::pack2(0.f, 0.f)), s[nt][2 * i], s[nt][2 * i + 1]);
       }
       // row-major [query][key], one 32-bit store per key pair (conflict-free: 36-word pitch)
       __nv_bfloat16* p0 = sP + (warp * 16 + g) * TP + nt * 8 + 2 * t;
