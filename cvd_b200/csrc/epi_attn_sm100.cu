@@ -60,23 +60,35 @@ struct Cfg {
   static constexpr int kKBytes = kKBlocks * kTileN * 128;
   static constexpr int kVBytes = kDV * 128;
   // TMEM: S [0,64) | O [64,64+DV) in the main allocation.  P (32 columns of packed bf16):
-  //   d=40 : second 32-column allocation (128 + 32 columns per CTA -> 3 CTAs per SM)
+  //   d=40 : aliased onto S inside one 128-column allocation -> 4 CTAs per SM (see kFour below)
   //   d=80 : behind O inside a 256-column allocation
   //   d=160: aliased onto S (then Q K^T of tile j+1 has to follow P_j V_j)
   static constexpr int kColS = 0, kColO = kTileN;
-  static constexpr bool kAliasP = (kColO + kDV + kTileN / 2) > 256;
+  // d <= 48 ("kFour"): S 64 + O 48 columns fit ONE 128-column allocation if P is written in place over S, so FOUR CTAs
+  // (16 softmax warps) share an SM at 96 registers per thread -- the fused softmax loop then takes its scores from TMEM
+  // 16 at a time.  Measured at the bench shape: 204 us against 222 us for three CTAs with P in its own 32 columns
+  // (128 registers, Q K^T of tile j+1 overlapping the softmax of tile j); 4096 CTAs are also 6.9 waves of 592 slots
+  // instead of 9.2 of 444.  make EXTRA=-DCVD_D40_THREE_CTAS rebuilds the three-CTA configuration for A/B runs.
+#ifdef CVD_D40_THREE_CTAS
+  static constexpr bool kFour = false;
+#else
+  static constexpr bool kFour = (kColO + kDV) <= 128;
+#endif
+  static constexpr bool kAliasP = kFour || (kColO + kDV + kTileN / 2) > 256;
   static constexpr bool kSplitP = !kAliasP && (kColO + kDV) <= 128;
-  static constexpr int kTmemCols = kSplitP ? 128 : 256;
+  static constexpr int kTmemCols = (kSplitP || kFour) ? 128 : 256;
   static constexpr int kColP = kAliasP ? kColS : (kSplitP ? 0 : kColO + kDV);   // kSplitP: relative to the 2nd allocation
   static_assert(kColO + kDV <= 256, "TMEM budget");
   // K/V ring depth (never deeper than the tile count)
-  static constexpr int kWant = D <= 40 ? 3 : (D <= 80 ? 2 : (kTiles > 1 ? 2 : 1));
+  static constexpr int kWant = kFour ? 2 : (D <= 40 ? 3 : (D <= 80 ? 2 : (kTiles > 1 ? 2 : 1)));
   static constexpr int kKStages = kWant < kTiles ? kWant : kTiles;
   static constexpr int kVStages = kKStages;
   static constexpr int kSmemData = kQBytes + kKStages * kKBytes + kVStages * kVBytes;
-  // d=40 must NOT fit a 4th CTA (4 x 128 TMEM columns would starve the 32-column allocations)
-  static constexpr int kSmemBytes = (kSplitP && kSmemData < 58 * 1024 ? 58 * 1024 : kSmemData) + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kMinBlocks = kSplitP ? 3 : (kSmemBytes <= 110 * 1024 ? 2 : 1);
+  // three-CTA build: d=40 must NOT fit a 4th CTA (4 x 128 TMEM columns would starve the 32-column allocations);
+  // four-CTA build: must not fit a 5th (no TMEM left for it)
+  static constexpr int kSmemFloor = kSplitP ? 58 * 1024 : (kFour ? 47 * 1024 : 0);
+  static constexpr int kSmemBytes = (kSmemData < kSmemFloor ? kSmemFloor : kSmemData) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kMinBlocks = kFour ? 4 : (kSplitP ? 3 : (kSmemBytes <= 110 * 1024 ? 2 : 1));
 };
 
 struct Barriers {
@@ -334,9 +346,12 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // magnitude), and everything older is rescaled as before.  The second half of S is fetched under block 0.
         constexpr int kQ = 16;
         uint32_t s0[kHalfN], s1[kHalfN];
-        tmem_ld_x32(tS, s0);
-        tmem_ld_wait();
-        if (DBG && j == 0) {
+        uint32_t sq[kQ];
+        if (!C::kFour) {
+          tmem_ld_x32(tS, s0);
+          tmem_ld_wait();
+        }
+        if (DBG && j == 0 && !C::kFour) {
           float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kTileN;
 #pragma unroll
           for (int c = 0; c < kHalfN; ++c) o[c] = __uint_as_float(s0[c]);
@@ -344,8 +359,17 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          uint32_t* cur = (q < 2 ? s0 : s1) + (q & 1) * kQ;                 // scores -> x of quarter q (in place)
-          if (q == 0) tmem_ld_x32(tS + kHalfN, s1);                          // lands under this block
+          uint32_t* cur = C::kFour ? sq : ((q < 2 ? s0 : s1) + (q & 1) * kQ);   // scores -> x of quarter q (in place)
+          if (C::kFour) {                                                    // 96-register build: 16 scores at a time
+            tmem_ld_x16(tS + q * kQ, sq);
+            tmem_ld_wait();
+            if (DBG && j == 0) {
+              float* o = dbg + ((size_t)blockIdx.x * kBlockM + tid) * kTileN + q * kQ;
+#pragma unroll
+              for (int c = 0; c < kQ; ++c) o[c] = __uint_as_float(sq[c]);
+            }
+          }
+          if (q == 0 && !C::kFour) tmem_ld_x32(tS + kHalfN, s1);             // lands under this block
           const float bm = bandp - m_used, negm = -m_used;
           float xmax = -INFINITY;
           uint64_t a1 = 0, a2 = 0;
@@ -372,7 +396,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             a1 = add2(a1, step1);
             a2 = add2(a2, step2);
           }
-          if (q == 0) {
+          if (q == 0 && !C::kFour) {
             tmem_ld_wait_dep32(s1);
             if (!C::kAliasP && !kNoSync) {      // S_j is in registers: the tensor core may start Q K_{j+1}^T
               tc_fence_before();
@@ -985,10 +1009,9 @@ static int launch_wg2(const void* q, const void* k, const void* vt, const float*
   return CVD_OK;
 }
 
-// Measured (R = 64 / 16 rows, d = 40): 64x64 latents 808 vs 848 us (the two-warpgroup variant wins by 5 %), 32x32 240 vs
-// 234 us, 16x16 28.3 vs 26.2 us (it loses: with P aliased on S each chain is longer, and the two chains of a CTA are
-// coupled through the single in-order issuer).  Default: wg2 for feat >= 64 only.  CVD_ATTN_WG2=1 forces it wherever
-// it is instantiated, CVD_ATTN_WG2=0 disables it (A/B measurements).
+// Measured (R = 64 / 16 rows, d = 40) against the three-CTA kernel: 64x64 latents 808 vs 848 us, 32x32 240 vs 234 us,
+// 16x16 28.3 vs 26.2 us.  The four-CTA configuration of the main kernel (Cfg::kFour) beats it everywhere (64x64: 754 us),
+// so it is opt-in now: CVD_ATTN_WG2=1 forces it wherever it is instantiated (A/B measurements, forced-variant test).
 static int wg2_mode() {
   static int v = -2;
   if (v == -2) {
@@ -1044,7 +1067,7 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
     if (feat == 64) return launch_pp<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
     if (feat == 16) return launch_pp<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
   }
-  if (dbg == nullptr && head_dim == 40 && (wg2_mode() == 1 || (wg2_mode() == -1 && feat >= 64))) {
+  if (dbg == nullptr && head_dim == 40 && wg2_mode() == 1) {
     if (feat == 32) return launch_wg2<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
     if (feat == 64) return launch_wg2<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
     if (feat == 16) return launch_wg2<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);

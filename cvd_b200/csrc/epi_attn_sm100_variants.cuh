@@ -367,9 +367,10 @@ struct BarriersC {
 template <int D, int FEAT>
 struct CfgC {
   using B = Cfg<D, FEAT>;
-  static_assert(B::kSplitP && B::kKBlocks == 1, "cs variant: d <= 48 (P in its own TMEM allocation)");
+  static_assert(B::kColO + B::kDV <= 128 && B::kKBlocks == 1, "cs variant: d <= 48 (S + O in 128 columns, P in its own 32)");
   static_assert(B::kN % kTileN == 0, "cs variant: whole key tiles");
-  static constexpr int kSmemBytes = B::kSmemBytes + 2048;
+  // three CTAs per SM (128 + 32 TMEM columns each): a fourth must not fit
+  static constexpr int kSmemBytes = (B::kSmemData < 58 * 1024 ? 58 * 1024 : B::kSmemData) + 1024 + 256 + 2048;
 };
 
 template <int D, int FEAT>
