@@ -62,7 +62,7 @@ def load_peaks():
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
     committed ncu --set full capture of this round (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_epi_attn_d40_ncu_full_v6.json")
+    path = os.path.join(ROOT, "profiles", "r01_epi_attn_d40_ncu_full_v7.json")
     try:
         d = json.load(open(path))
         rd = float(d["dram__bytes_read.sum"].split()[0]) * 1e6
@@ -533,7 +533,7 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "epi_attn_fwd_kernel<40,32> (R=64, N=M=1024, C=320)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes per launch (ncu, profiles/r01_epi_attn_d40_ncu_full_v6.json)",
+                         "traffic": ncu_traffic_bytes(), "traffic_unit": "bytes per launch (ncu, profiles/r01_epi_attn_d40_ncu_full_v7.json)",
                          "peak_source": peak_src, "ms_per_launch": big_ms,
                          "algorithmic_flops_per_launch": big_flops},
             "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
