@@ -16,11 +16,12 @@
 //  * Measured on B200 (profiles/r01_summary.md): at d=40 the kernel sits between the hand-off latencies (every mbarrier /
 //    TMEM round trip costs 100-350 cycles, a tcgen05.mma / commit 50-100 cycles of the issuing warp) and the softmax
 //    instruction stream (11-12 scheduler cycles per warp-column in the kernel, MUFU floor 8).  Hence: few, 64-key MMA
-//    rounds; P in its own TMEM columns so Q K^T of tile j+1 is issued as soon as S_j has been read, overlapping the
-//    softmax of tile j; THREE CTAs resident per SM at d=40 (TMEM 128 + 32 columns each) covering each other's latencies.
+//    rounds, and as many chains per SM as TMEM and registers allow: d=40 runs FOUR CTAs per SM (S + O in one 128-column
+//    allocation, P in place over S, 96 registers; see Cfg::kFour), d=80 two (P in its own columns, so Q K^T of tile j+1 is
+//    issued as soon as S_j has been read and overlaps the softmax of tile j), d=160 one or two.
 //  * Warp roles per CTA (160 threads): warps 0-3 softmax (one TMEM lane quarter each), warp 4 TMA producer + MMA issuer +
-//    TMEM owner (one elected lane issues).  Five warps, not six: 3 CTAs are then 15 warps per SM, 4 per scheduler at most,
-//    which leaves 128 registers per thread for the fused softmax loop (18 warps: 96, and it spilled).
+//    TMEM owner (one elected lane issues).  Five warps, not six: the per-scheduler warp count sets the register budget
+//    (20 warps per SM: 96 registers; 15: 128; the six-warp layout allowed 80 / 96 and the fused softmax loop spilled).
 //  * Softmax loop: a tile is walked in four 16-key quarters; in each, every score goes bias -> FFMA2 -> MUFU.EX2 -> F2FP
 //    in one straight-line block (ptxas interleaves the MUFU stream with the FADD2 / FMNMX3 stream only through such true
 //    dependencies), and the reference-maximum vote follows the exponentials.
