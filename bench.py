@@ -349,6 +349,13 @@ def run_ours(args):
     side_stream = torch.cuda.Stream()
     ev_b, ev_c = torch.cuda.Event(), [torch.cuda.Event() for _ in range(4)]
     chunks, whole = [(0, R // 2), (R // 2, R)], [(0, R)]
+    # 32x32, d = 40: four CTAs per SM = 592 slots, 64 CTAs per row -> 9.25 rows per wave.  Whole waves per chunk, the
+    # smaller chunk first (its transfer is the exposed one): 27 rows = 3 waves, 37 rows = 4 waves (32 + 32 would be 4 + 4)
+    rpw = 148 * 4 / (HEADS * (32 * 32 // 128))
+    n_w = int(np.ceil(R / rpw))
+    r0 = int((n_w // 2) * rpw)
+    chunks32 = [(0, r0), (r0, R)] if 0 < r0 < R else chunks
+    runs32 = None
     quarters = [(i * R // 4, (i + 1) * R // 4) for i in range(4)]
     runs = runs_whole = runs_q = None
     if shard is not None:
@@ -366,6 +373,7 @@ def run_ours(args):
         partner_local = (partner % R).to(torch.int32)      # row inside the source rank's buffer
         runs = [runs_of(lo, hi) for lo, hi in chunks]
         runs_q = [runs_of(lo, hi) for lo, hi in quarters]
+        runs32 = [runs_of(lo, hi) for lo, hi in chunks32]
         runs_whole = runs_of(0, R)
 
     def value_step(record):
@@ -394,9 +402,9 @@ def run_ours(args):
                         side_stream.wait_event(ev_b)
                         # small grids: one transfer, one attention launch (four 16-row chunks at 32x32 measured slower:
                         # 6.28 vs 6.19 ms per step on 2 GPUs, the quarter-size attention grids lose more than the overlap gains)
-                        use = chunks if feat >= 16 else whole
+                        use = (chunks32 if feat == 32 else chunks) if feat >= 16 else whole
                         for c, (lo, hi) in enumerate(use):
-                            for (dlo, dhi, src_rank, slo) in (runs_q[c] if use is quarters else (runs[c] if use is chunks else runs_whole)):
+                            for (dlo, dhi, src_rank, slo) in (runs_q[c] if use is quarters else (runs32[c] if use is chunks32 else (runs[c] if use is chunks else runs_whole))):
                                 ld[0][dlo:dhi].copy_(xk[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
                                 ld[1][dlo:dhi].copy_(xv[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
                             ev_c[c].record(side_stream)
