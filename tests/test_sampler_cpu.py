@@ -152,11 +152,12 @@ def _mv_inputs(V):
     return lat, text, Fm, poses
 
 
-def _run_mv(lat, text, Fm, poses, shard, unet, seed):
+def _run_mv(lat, text, Fm, poses, shard, unet, seed, kv_on_device=False):
     np.random.seed(seed)
     torch.manual_seed(seed)
     return sampler.sample_multiview(unet, lat, text, sampler.DDIMSchedule(), 4, 8.5, F_mats=Fm,
-                                    pose_embedding_features=poses, multistep=2, accumulate_step=2, shard=shard)
+                                    pose_embedding_features=poses, multistep=2, accumulate_step=2, shard=shard,
+                                    kv_on_device=kv_on_device)
 
 
 def _worker(rank, world, port, ret):
@@ -171,6 +172,10 @@ def _worker(rank, world, port, ret):
         unet = ToyUNet(gather=shard.gather_rows)
         out = _run_mv(lat[loc].clone(), text[2 * rank:2 * rank + 2], Fm, [p[loc] for p in poses], shard, unet, 11)
         ret[rank] = out.numpy()
+        # kv_index handed over as an int32 tensor (what a CUDA-graphed UNet needs): same result
+        unet2 = ToyUNet(gather=shard.gather_rows)
+        out2 = _run_mv(lat[loc].clone(), text[2 * rank:2 * rank + 2], Fm, [p[loc] for p in poses], shard, unet2, 11, True)
+        assert torch.equal(out, out2)
     finally:
         dist.destroy_process_group()
 
