@@ -166,7 +166,7 @@ def run_reference(args):
     if rank != 0:
         return
     R = R_PER_GPU * args.gpus
-    warm = min(args.warmup, 1)
+    warm = args.warmup
     times, flops, cores = cpu_reference_step(R, args.steps, warm)
     total = sum(times)
     val = flops * len(times) / total / 1e12
@@ -297,7 +297,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     shard = peer = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: if the caller asks for NCCL logging (NCCL_DEBUG=INFO, e.g. to count
+        # ranks / see NVLS) it goes to stderr instead of being silenced
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
         if args.exchange in ("peer", "dma"):

@@ -28,7 +28,6 @@ SIGNATURES = {
     "cvd_epi_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_simt": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_debug": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
-    "cvd_epi_attn_pp_profile_dump": [],
     "cvd_groupnorm_tokens_fwd": [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "cvd_layernorm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
     "cvd_residual_layernorm_fwd": [_P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _F, _P],
@@ -40,6 +39,7 @@ SIGNATURES = {
     "cvd_scale_add_fwd": [_P, _P, _F, _P, _LL, _P],
     "cvd_peer_gather_rows": [_P, _I, _P, _P, _I, _I, _LL, _P],
     "cvd_pairwise_fundamental": [_P, _P, _P, _P, _I, _P],
+    "cvd_plucker_embedding": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
 }
 
 _lib = None

@@ -1,5 +1,8 @@
 // Error reporting and versioning of the C ABI (include/cvd_b200.h).
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -25,6 +28,24 @@ bool pdl_enabled() {
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest value set for every
+// (kernel, device) so that a process driving several GPUs configures each of them (grow-only, thread-safe).
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[std::make_pair(kernel, dev)];
+  if (bytes > have) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    have = bytes;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace cvd

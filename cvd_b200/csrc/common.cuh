@@ -37,6 +37,9 @@ int fail(int code, const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (once per kernel and device)
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

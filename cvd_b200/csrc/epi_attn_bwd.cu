@@ -334,11 +334,7 @@ static int launch(const void* q, const void* k, const void* v, const float* rowp
                   const float* lse, const float* delta, float* dq, float* dk, float* dv, int R, int N, int H, int feat, float S,
                   cudaStream_t st) {
   using Cf = CfgB<D, BLK>;
-  static bool configured = false;
-  if (!configured) {
-    CVD_CUDA(cudaFuncSetAttribute(epi_attn_bwd_kernel<D, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cf::kSmem));
-    configured = true;
-  }
+  CVD_CUDA(ensure_dynamic_smem((const void*)epi_attn_bwd_kernel<D, BLK>, Cf::kSmem));
   dim3 grid((unsigned)((N / BLK) * Cf::kChunks), (unsigned)H, (unsigned)R);
   epi_attn_bwd_kernel<D, BLK><<<grid, Cf::kWarps * 32, Cf::kSmem, st>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, rowp, partner, (const __nv_bfloat16*)d_o, lse,

@@ -30,6 +30,9 @@
 //    (the subtraction is folded into the bias terms) and O is rescaled only when a score
 //    exceeds it by more than 2^16 (rare).
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -577,320 +580,6 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 
 // ------------------------------------------------------------------------------------------
-// d = 40 variant with TWO softmax warpgroups per CTA ("wg2").  Measured on the kernel above (profiles/): the softmax
-// warps spend ~27 % of their time waiting at hand-offs and three chains per SM are all that its TMEM budget
-// (S 64 + O 48 + P 32 columns per chain) allows.  Here a CTA keeps its 128 queries but runs TWO chains over them:
-// warpgroup g takes the key tiles j = g (mod 2), with its own score buffer S_g, its own accumulator O_g (its own
-// reference maximum and denominator) and P_g aliased onto S_g -- 2 x (64 + 48) = 224 TMEM columns, two CTAs = four
-// chains and 16 softmax warps per SM inside 2 x 320 threads x 96 registers.  While warpgroup 0 works on tile j the
-// tensor core forms S of tile j+1 for warpgroup 1; the two partial results meet once, in the epilogue:
-//   out = (2^(m0-m) O_0 + 2^(m1-m) O_1) / (2^(m0-m) l_0 + 2^(m1-m) l_1),  m = max(m0, m1).
-// Warps 0-3 / 4-7 softmax (lane quarter = warp & 3), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner.
-// ------------------------------------------------------------------------------------------
-constexpr int kThreadsW = 320;
-
-template <int D, int FEAT>
-struct CfgW {
-  static_assert(D <= 48 && D % 8 == 0, "wg2 variant: head_dim <= 48");
-  static constexpr int kN = FEAT * FEAT;
-  static constexpr int kTiles = (kN + kTileN - 1) / kTileN;
-  static_assert(kN % kTileN == 0 && kTiles >= 2, "wg2 variant: at least two full key tiles per partner");
-  static constexpr int kKSteps = (D + 15) / 16;
-  static constexpr int kDV = (D / 16 + 1) * 16;
-  static constexpr int kQBytes = kBlockM * 128, kKBytes = kTileN * 128, kVBytes = kDV * 128;
-  static constexpr int kColS = 0, kColO = 2 * kTileN;           // S_g at g*64, O_g at 128 + g*kDV
-  static_assert(kColO + 2 * kDV <= 256, "TMEM budget");
-  static constexpr int kStages = kTiles < 4 ? kTiles : 4;
-  static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + 1024 /*align slack*/ + 1536 /*barriers + mref*/;
-};
-
-struct BarriersW {
-  uint64_t q_full, s_full[2], p_full[2], pv_done[2], o_done[2];
-  uint64_t k_full[4], k_empty[4], v_full[4], v_empty[4];
-  uint32_t tmem_base;
-  float mref[2][kBlockM];      // final reference maxima of the two chains (epilogue merge)
-};
-
-template <int D, int FEAT>
-__global__ void __launch_bounds__(kThreadsW, 2)
-epi_attn_fwd_wg2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                        const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
-                        const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R, int H, int n_partners,
-                        float step, float* __restrict__ lse) {
-  using C = CfgW<D, FEAT>;
-  constexpr int N = C::kN;
-  constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
-  constexpr int kRowsPerTile = (kTileN + FEAT - 1) / FEAT;
-  constexpr uint32_t kIdescQK = umma_idesc_bf16(kBlockM, kTileN);
-  constexpr uint32_t kIdescPV = umma_idesc_bf16(kBlockM, C::kDV);
-
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sK = sQ + C::kQBytes;
-  const uint32_t sV = sK + C::kStages * C::kKBytes;
-  BarriersW* bars = reinterpret_cast<BarriersW*>(smem_raw + (sV + C::kStages * C::kVBytes - smem_u32(smem_raw)));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % kQTiles;
-  const int h = (blockIdx.x / kQTiles) % H;
-  const int r = blockIdx.x / (kQTiles * H);
-  const int total = n_partners * C::kTiles;        // >= 2: both chains have work
-
-  if (warp == 8 && lane == 0) {
-    prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmK);
-    prefetch_tmap(&tmV);
-    mbar_init(smem_u32(&bars->q_full), 1);
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(smem_u32(&bars->s_full[g]), 1);
-      mbar_init(smem_u32(&bars->p_full[g]), 128);
-      mbar_init(smem_u32(&bars->pv_done[g]), 1);
-      mbar_init(smem_u32(&bars->o_done[g]), 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(smem_u32(&bars->k_full[i]), 1);
-      mbar_init(smem_u32(&bars->k_empty[i]), 1);
-      mbar_init(smem_u32(&bars->v_full[i]), 1);
-      mbar_init(smem_u32(&bars->v_empty[i]), 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 9) tmem_alloc<256>(smem_u32(&bars->tmem_base));
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
-
-  if (warp == 8) {
-    // =============================== TMA producer ===============================
-    if (elect_one()) {
-      mbar_expect_tx(smem_u32(&bars->q_full), C::kQBytes);
-      tma_load_3d(sQ, &tmQ, 0, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
-    }
-    for (int lt = 0; lt <= total; ++lt) {
-      if (lt < total) {       // K tile lt (one tile ahead of V)
-        const int p = lt / C::kTiles, j = lt % C::kTiles;
-        const int rr = partner[p * R + r];
-        const int st = lt % C::kStages;
-        if (lt >= C::kStages) mbar_wait(smem_u32(&bars->k_empty[st]), ((lt / C::kStages) - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
-          tma_load_3d(sK + st * C::kKBytes, &tmK, 0, h, rr * N + j * kTileN, smem_u32(&bars->k_full[st]));
-        }
-      }
-      if (lt >= 1) {          // V^T tile lt-1
-        const int lv = lt - 1;
-        const int p = lv / C::kTiles, j = lv % C::kTiles;
-        const int rr = partner[p * R + r];
-        const int st = lv % C::kStages;
-        if (lv >= C::kStages) mbar_wait(smem_u32(&bars->v_empty[st]), ((lv / C::kStages) - 1) & 1);
-        if (elect_one()) {
-          mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
-          tma_load_2d(sV + st * C::kVBytes, &tmV, j * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
-        }
-      }
-      __syncwarp();
-    }
-  } else if (warp == 9) {
-    // =============================== MMA issuer =================================
-    // issue order: QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...   (P_g aliases S_g: QK(j+2) follows PV(j);
-    // tcgen05.mma executes in issue order)
-    auto issue_qk = [&](int j) {
-      const int st = j % C::kStages, g = j & 1;
-      mbar_wait(smem_u32(&bars->k_full[st]), (j / C::kStages) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < C::kKSteps; ++ks)
-          umma_ss(tmem + C::kColS + g * kTileN, umma_desc_k_sw128(sQ + ks * 32), umma_desc_k_sw128(sK + st * C::kKBytes + ks * 32),
-                  kIdescQK, ks > 0);
-        umma_commit(smem_u32(&bars->s_full[g]));
-        umma_commit(smem_u32(&bars->k_empty[st]));
-      }
-      __syncwarp();
-    };
-    mbar_wait(smem_u32(&bars->q_full), 0);
-    issue_qk(0);
-    issue_qk(1);
-    for (int j = 0; j < total; ++j) {
-      const int st = j % C::kStages, g = j & 1, i = j >> 1;
-      mbar_wait(smem_u32(&bars->v_full[st]), (j / C::kStages) & 1);
-      mbar_wait(smem_u32(&bars->p_full[g]), i & 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < kTileN / 16; ++ks)
-          umma_ts(tmem + C::kColO + g * C::kDV, tmem + C::kColS + g * kTileN + ks * 8,
-                  umma_desc_k_sw128(sV + st * C::kVBytes + ks * 32), kIdescPV, (i > 0) || (ks > 0));
-        umma_commit(smem_u32(&bars->pv_done[g]));
-        if (j + 2 >= total) umma_commit(smem_u32(&bars->o_done[g]));     // last tile of chain g
-        umma_commit(smem_u32(&bars->v_empty[st]));
-      }
-      __syncwarp();
-      if (j + 2 < total) issue_qk(j + 2);
-    }
-  } else {
-    // =============================== softmax warpgroups =========================
-    const int g = warp >> 2;                               // chain
-    const int tid = threadIdx.x & 127;                     // query row inside the tile == TMEM lane
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem + lane_off + C::kColS + g * kTileN, tO = tmem + lane_off + C::kColO + g * C::kDV;
-    int n = qt * kBlockM + tid;
-    const bool row_valid = n < N;
-    if (!row_valid) n = N - 1;
-    const float xq = pixel_centre(n % FEAT, step), yq = pixel_centre(n / FEAT, step);
-    const float off = (step - 1.0f) * 0.5f;
-    const float scale_log2 = kLog2e * rsqrtf((float)D);
-    float As = 0.f, Bs = 0.f, base = 0.f, bandp = 0.f;
-    float m_used = 0.f, bias_ub = 0.f;
-    const uint64_t scale2 = pack2(scale_log2, scale_log2);
-    int cur_p = -1;
-
-    for (int j = g; j < total; j += 2) {
-      const int i = j >> 1;                                // tile counter of this chain
-      const int p = j / C::kTiles, jj = j % C::kTiles;
-      if (p != cur_p && rowp != nullptr) {                 // first tile of this chain inside partner p's key range
-        cur_p = p;
-        const float* P = rowp + (size_t)(p * R + r) * CVD_ROWP_STRIDE;
-        const float a = fmaf(P[1], yq, P[0] * xq) + P[2];
-        const float b = fmaf(P[4], yq, P[3] * xq) + P[5];
-        const float c = fmaf(P[7], yq, P[6] * xq) + P[8];
-        const float k1 = P[10] * kLog2e / (sqrtf(a * a + b * b) + 1e-6f);
-        const float A = a * k1, B = b * k1;
-        As = A * step;
-        Bs = B * step;
-        base = fmaf(A, off, fmaf(B, off, c * k1));
-        bandp = P[9] * P[10] * kLog2e;
-        if (i == 0) {
-          const float e = (float)(FEAT - 1);
-          const float t00 = base, t10 = fmaf(As, e, base), t01 = fmaf(Bs, e, base), t11 = fmaf(As, e, t01);
-          const float lo = fminf(fminf(t00, t10), fminf(t01, t11)), hi = fmaxf(fmaxf(t00, t10), fmaxf(t01, t11));
-          const float tmin = (lo <= 0.f && hi >= 0.f) ? 0.f : fminf(fabsf(lo), fabsf(hi));
-          bias_ub = fminf(bandp - tmin, 0.f);
-        }
-      }
-      mbar_wait(smem_u32(&bars->s_full[g]), i & 1);
-      tc_fence_after();
-
-      uint32_t preg[kTileN / 2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t sreg[kHalfN];
-        tmem_ld_x32(tS + hh * kHalfN, sreg);
-        tmem_ld_wait();
-        const float bm = bandp - m_used, negm = -m_used;
-        const uint64_t step1 = pack2(-2.f * As, -2.f * As), step2 = pack2(2.f * As, 2.f * As);
-        float xmax = -INFINITY;
-        uint64_t a1 = 0, a2 = 0;
-#pragma unroll
-        for (int c = 0; c < kHalfN; c += 2) {
-          const int cc = hh * kHalfN + c;
-          if (cc % FEAT == 0 || c == 0) {
-            const float rb = fmaf(Bs, (float)(jj * kRowsPerTile + cc / FEAT), base);
-            const float t0 = fmaf(As, (float)(cc % FEAT), rb);
-            a1 = pack2(bm - t0, bm - t0 - As);
-            a2 = pack2(bm + t0, bm + t0 + As);
-          }
-          float a1x, a1y, a2x, a2y;
-          unpack2(a1, a1x, a1y);
-          unpack2(a2, a2x, a2y);
-          const float v0 = min3(a1x, a2x, negm), v1 = min3(a1y, a2y, negm);
-          float x0, x1;
-          unpack2(fma2(pack2(__uint_as_float(sreg[c]), __uint_as_float(sreg[c + 1])), scale2, pack2(v0, v1)), x0, x1);
-          xmax = max3(xmax, x0, x1);
-          sreg[c] = __float_as_uint(x0);
-          sreg[c + 1] = __float_as_uint(x1);
-          a1 = add2(a1, step1);
-          a2 = add2(a2, step2);
-        }
-        const bool first = (i == 0 && hh == 0);
-        const bool need = first || (xmax > kRescaleThreshold);
-        if (__any_sync(0xffffffffu, need)) {
-          if (!first) {
-            const float f = need ? ex2(-xmax) : 1.0f;
-            if (i > 0) {     // O_g holds this chain's tiles 0..i-1: its previous P V must have landed
-              mbar_wait(smem_u32(&bars->pv_done[g]), (i - 1) & 1);
-              tc_fence_after();
-#pragma unroll
-              for (int c0 = 0; c0 < C::kDV; c0 += 16) {
-                uint32_t o[16];
-                tmem_ld_x16(tO + c0, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 16; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * f);
-                tmem_st_x16(tO + c0, o);
-              }
-            }
-            if (hh == 1) {
-#pragma unroll
-              for (int q = 0; q < kHalfN / 2; ++q)
-                preg[q] = pack_bf16(__uint_as_float(preg[q] << 16) * f, __uint_as_float(preg[q] & 0xffff0000u) * f);
-            }
-          }
-          if (need) {
-            const float shift = first ? fmaxf(xmax, bias_ub) : xmax;
-            m_used += shift;
-#pragma unroll
-            for (int c = 0; c < kHalfN; ++c) sreg[c] = __float_as_uint(__uint_as_float(sreg[c]) - shift);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < kHalfN; c += 2)
-          preg[hh * (kHalfN / 2) + (c >> 1)] = pack_bf16(ex2(__uint_as_float(sreg[c])), ex2(__uint_as_float(sreg[c + 1])));
-      }
-      // P_g over the first 32 columns of S_g (both halves of S_g are in registers / consumed; s_full(j) implies that
-      // P V of this chain's previous tile has finished reading the old P)
-      tmem_st_x32(tS, preg);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[g]));
-    }
-
-    // ---- epilogue: merge the two chains -------------------------------------------------
-    bars->mref[g][tid] = m_used;
-    mbar_wait(smem_u32(&bars->o_done[0]), 0);
-    mbar_wait(smem_u32(&bars->o_done[1]), 0);
-    tc_fence_after();
-    asm volatile("bar.sync 1, 256;" ::: "memory");         // the eight softmax warps: both reference maxima are visible
-    const float m0 = bars->mref[0][tid], m1 = bars->mref[1][tid];
-    const float mm = fmaxf(m0, m1);
-    const float f0 = ex2(m0 - mm), f1 = ex2(m1 - mm);
-    const uint32_t tO0 = tmem + lane_off + C::kColO, tO1 = tO0 + C::kDV;
-    uint32_t l0raw, l1raw;
-    tmem_ld_x1(tO0 + D, l0raw);
-    tmem_ld_x1(tO1 + D, l1raw);
-    tmem_ld_wait();
-    const float lsum = fmaf(__uint_as_float(l0raw), f0, __uint_as_float(l1raw) * f1);
-    const float inv = 1.0f / lsum;
-    const float w0 = f0 * inv, w1 = f1 * inv;
-    if (lse != nullptr && row_valid && g == 0) lse[((size_t)r * H + h) * N + n] = mm + log2f(lsum);
-    __nv_bfloat16* orow = out + ((size_t)r * N + n) * (size_t)(H * D) + h * D;
-    // 8-column chunks of the output row, split between the two warpgroups
-    constexpr int kChunks = D / 8, kHalfChunks = (kChunks + 1) / 2;
-    const int cbeg = g == 0 ? 0 : kHalfChunks, cend = g == 0 ? kHalfChunks : kChunks;
-    for (int ch = cbeg; ch < cend; ++ch) {
-      uint32_t a[8], b[8];
-      tmem_ld_x8(tO0 + ch * 8, a);
-      tmem_ld_x8(tO1 + ch * 8, b);
-      tmem_ld_wait();
-      uint4 pk;
-      pk.x = pack_bf16(fmaf(__uint_as_float(a[0]), w0, __uint_as_float(b[0]) * w1), fmaf(__uint_as_float(a[1]), w0, __uint_as_float(b[1]) * w1));
-      pk.y = pack_bf16(fmaf(__uint_as_float(a[2]), w0, __uint_as_float(b[2]) * w1), fmaf(__uint_as_float(a[3]), w0, __uint_as_float(b[3]) * w1));
-      pk.z = pack_bf16(fmaf(__uint_as_float(a[4]), w0, __uint_as_float(b[4]) * w1), fmaf(__uint_as_float(a[5]), w0, __uint_as_float(b[5]) * w1));
-      pk.w = pack_bf16(fmaf(__uint_as_float(a[6]), w0, __uint_as_float(b[6]) * w1), fmaf(__uint_as_float(a[7]), w0, __uint_as_float(b[7]) * w1));
-      if (row_valid) *reinterpret_cast<uint4*>(orow + ch * 8) = pk;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc<256>(tmem);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -909,21 +598,55 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Encoded descriptors are cached per (base pointer, shape, box): a UNet forward issues the same 40 (q, k, v^T) triples
+// every denoising step (PyTorch's caching allocator hands the same blocks back), so steady-state launches do no driver
+// calls.  A descriptor only encodes address and geometry, so a stale entry for a recycled pointer is still correct.
+struct MapKey {
+  const void* base;
+  uint64_t a, b, c;
+  uint32_t box_rows, kind;
+  bool operator<(const MapKey& o) const {
+    return std::tie(base, a, b, c, box_rows, kind) < std::tie(o.base, o.a, o.b, o.c, o.box_rows, o.kind);
+  }
+};
+static std::mutex g_map_mu;
+static std::map<MapKey, CUtensorMap> g_maps;
+
+template <typename Encode>
+static int cached_map(CUtensorMap* m, const MapKey& key, Encode&& encode) {
+  {
+    std::lock_guard<std::mutex> lock(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *m = it->second;
+      return CVD_OK;
+    }
+  }
+  const int rc = encode();
+  if (rc != CVD_OK) return rc;
+  std::lock_guard<std::mutex> lock(g_map_mu);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps[key] = *m;
+  return CVD_OK;
+}
+
 // 2-D bf16 tensor [rows, cols] (cols contiguous), box [box_rows, 64 cols], 128-byte swizzle
 static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[2] = {64, box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS)
-    return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)rc,
-                (unsigned long long)rows, (unsigned long long)cols, box_rows);
-  return CVD_OK;
+  return cached_map(m, MapKey{base, rows, cols, 0, box_rows, 2}, [&]() -> int {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+      return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)rc,
+                  (unsigned long long)rows, (unsigned long long)cols, box_rows);
+    return CVD_OK;
+  });
 }
 
 // bf16 projections [rows, heads * d] seen as 3-D [rows, heads, d]; box [box_rows, 1 head, 64 columns], 128-byte
@@ -931,19 +654,21 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
 // d are out of bounds of the innermost dimension and are filled with zeros by the TMA unit, so the K padding of
 // the MMA needs no patching and no bytes of the neighbouring head are fetched.
 static int make_map_heads(CUtensorMap* m, const void* base, uint64_t rows, uint64_t heads, uint64_t d, uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[3] = {d, heads, rows};
-  const cuuint64_t strides[2] = {d * sizeof(__nv_bfloat16), heads * d * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[3] = {64, 1, box_rows};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS)
-    return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%llu heads=%llu d=%llu box_rows=%u)",
-                (int)rc, (unsigned long long)rows, (unsigned long long)heads, (unsigned long long)d, box_rows);
-  return CVD_OK;
+  return cached_map(m, MapKey{base, rows, heads, d, box_rows, 3}, [&]() -> int {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[3] = {d, heads, rows};
+    const cuuint64_t strides[2] = {d * sizeof(__nv_bfloat16), heads * d * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[3] = {64, 1, box_rows};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+      return fail(CVD_E_CUDA, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d (rows=%llu heads=%llu d=%llu box_rows=%u)",
+                  (int)rc, (unsigned long long)rows, (unsigned long long)heads, (unsigned long long)d, box_rows);
+    return CVD_OK;
+  });
 }
 
 template <int D, int FEAT>
@@ -967,11 +692,7 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug, true>
                                             : (pipe ? epi_attn_fwd_kernel<D, FEAT, false, true>
                                                     : epi_attn_fwd_kernel<D, FEAT, false, !kHasDebug>);
-  static bool configured[2] = {false, false};   // one process per GPU: set the attribute once per kernel
-  if (!configured[dbg != nullptr]) {
-    CVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured[dbg != nullptr] = true;
-  }
+  CVD_CUDA(ensure_dynamic_smem((const void*)kern, C::kSmemBytes));
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
@@ -982,68 +703,6 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
 }
 
 
-
-#include "epi_attn_sm100_variants.cuh"   // opt-in ping-pong / column-split variants (A/B measurements)
-
-template <int D, int FEAT>
-static int launch_wg2(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                      int R_kv, int H, int n_partners, float S, float* lse, cudaStream_t st) {
-  using C = CfgW<D, FEAT>;
-  constexpr int N = FEAT * FEAT;
-  CUtensorMap tmQ, tmK, tmV;
-  int rc;
-  if ((rc = make_map_heads(&tmQ, q, (uint64_t)R * N, (uint64_t)H, (uint64_t)D, kBlockM)) != CVD_OK) return rc;
-  if ((rc = make_map_heads(&tmK, k, (uint64_t)R_kv * N, (uint64_t)H, (uint64_t)D, kTileN)) != CVD_OK) return rc;
-  if ((rc = make_map(&tmV, vt, (uint64_t)R_kv * H * C::kDV, (uint64_t)N, C::kDV)) != CVD_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    CVD_CUDA(cudaFuncSetAttribute(epi_attn_fwd_wg2_kernel<D, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
-  }
-  constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
-  const long long grid = (long long)R * H * kQTiles;
-  CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
-  epi_attn_fwd_wg2_kernel<D, FEAT><<<(unsigned)grid, kThreadsW, C::kSmemBytes, st>>>(tmQ, tmK, tmV, rowp, partner,
-                                                                                  (__nv_bfloat16*)out, R, H, n_partners,
-                                                                                  S / (float)FEAT, lse);
-  CVD_LAUNCH_CHECK("epi_attn_fwd_wg2_kernel");
-  return CVD_OK;
-}
-
-// Measured (R = 64 / 16 rows, d = 40) against the three-CTA kernel: 64x64 latents 808 vs 848 us, 32x32 240 vs 234 us,
-// 16x16 28.3 vs 26.2 us.  The four-CTA configuration of the main kernel (Cfg::kFour) beats it everywhere (64x64: 754 us),
-// so it is opt-in now: CVD_ATTN_WG2=1 forces it wherever it is instantiated (A/B measurements, forced-variant test).
-static int wg2_mode() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("CVD_ATTN_WG2");
-    v = e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
-  }
-  return v;
-}
-
-// Measured (R = 64, d = 40, 32x32): ping-pong 240 us vs 222 us for the three-CTA kernel; 64x64 (R = 16) 917 vs 808 us.
-// Its cycle counters (CVD_ATTN_PP_PROF=1) show why: the softmax warps wait only 13 % of their loop, but with two warps
-// per scheduler the arithmetic itself runs at 12 cycles per warp-column (three warps: ~11, MUFU floor 8), so removing
-// the hand-off gaps does not pay for the lost third of the warps.  Kept for A/B measurements: CVD_ATTN_PP=1 enables it.
-static bool pp_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVD_ATTN_PP");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-// CVD_ATTN_CS=1 enables the column-split variant (A/B measurements until it is the default)
-static bool cs_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVD_ATTN_CS");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
 
 static int dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
                     int R_kv, int N, int heads, int head_dim, int n_partners, int feat, float S, float* dbg, float* lse,
@@ -1057,21 +716,6 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
   if (dbg == nullptr && feat <= 4) {   // 4x4 latent grid: warp-level kernel (a 128x64 tcgen05 tile would be 97 % padding; 6.5 vs 11 us)
     const int rc = epi_attn_small_dispatch(q, k, vt, rowp, partner, out, lse, R, heads, head_dim, n_partners, feat, S, st);
     if (rc != -1000) return rc;
-  }
-  if (dbg == nullptr && head_dim == 40 && cs_mode() && wg2_mode() != 1) {
-    if (feat == 32) return launch_cs<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 64) return launch_cs<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 16) return launch_cs<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-  }
-  if (dbg == nullptr && head_dim == 40 && pp_mode() && wg2_mode() != 1) {
-    if (feat == 32) return launch_pp<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 64) return launch_pp<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 16) return launch_pp<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-  }
-  if (dbg == nullptr && head_dim == 40 && wg2_mode() == 1) {
-    if (feat == 32) return launch_wg2<40, 32>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 64) return launch_wg2<40, 64>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
-    if (feat == 16) return launch_wg2<40, 16>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, lse, st);
   }
 #define CVD_CASE(D_, F_) \
   if (head_dim == D_ && feat == F_) return launch<D_, F_>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, dbg, lse, st);
@@ -1090,27 +734,6 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
 
 }  // namespace sm100
 }  // namespace cvd
-
-// Profiling aid (CVD_ATTN_PP_PROF=1): mean cycle counters of the last ping-pong launch to stderr.
-extern "C" int cvd_epi_attn_pp_profile_dump(void) {
-  using namespace cvd::sm100;
-  if (g_pp_prof == nullptr || g_pp_prof_used == 0) return cvd::fail(CVD_E_INVALID, "no profiled ping-pong launch");
-  CVD_CUDA(cudaDeviceSynchronize());
-  const size_t n = (size_t)g_pp_prof_used * 16;
-  long long* h = (long long*)malloc(n * sizeof(long long));
-  CVD_CUDA(cudaMemcpy(h, g_pp_prof, n * sizeof(long long), cudaMemcpyDeviceToHost));
-  double acc[16] = {0};
-  const long long lo = g_pp_prof_used / 4, hi = 3 * g_pp_prof_used / 4;
-  for (long long c = lo; c < hi; ++c)
-    for (int i = 0; i < 16; ++i) acc[i] += (double)h[c * 16 + i];
-  free(h);
-  const double k = 1.0 / (double)(hi - lo);
-  fprintf(stderr, "pp profile (mean cycles per CTA, middle half of the grid):\n");
-  for (int w = 0; w < 4; ++w) fprintf(stderr, "  softmax warp %d: s_full waits %.0f of %.0f loop cycles\n", w, acc[2 * w] * k, acc[2 * w + 1] * k);
-  fprintf(stderr, "  issuer: refills+k/v waits %.0f, p_full waits %.0f, PV issue %.0f, QK issue %.0f\n", acc[8] * k, acc[9] * k,
-          acc[10] * k, acc[11] * k);
-  return CVD_OK;
-}
 
 extern "C" int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, const float* rowp, const int* partner,
                                 void* out, int R, int R_kv, int N, int heads, int head_dim, int n_partners, int feat,

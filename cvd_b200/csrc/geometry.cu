@@ -27,16 +27,18 @@ __global__ void pairwise_fundamental_kernel(const double* __restrict__ c2w, cons
   const int t = partner[s];
   const double* Ms = c2w + (size_t)s * 16;
   const double* Mt = c2w + (size_t)t * 16;
-  // rigid inverse of the target pose: inv([R|p]) = [R^T | -R^T p]   (np.linalg.inv of a rigid 4x4)
-  double Rt[9], Rs[9], R[9], pt[3], ps[3], tr[3];
+  // inverse of the target pose as an affine map: inv([A|p]) = [A^-1 | -A^-1 p] -- what np.linalg.inv returns for any
+  // 4x4 with bottom row (0,0,0,1), orthonormal A or not (scaled / sheared user poses included)
+  double At[9], Ati[9], Rs[9], R[9], pt[3], ps[3], tr[3];
   for (int r = 0; r < 3; ++r) {
-    for (int c = 0; c < 3; ++c) { Rt[r * 3 + c] = Mt[c * 4 + r]; Rs[r * 3 + c] = Ms[r * 4 + c]; }
+    for (int c = 0; c < 3; ++c) { At[r * 3 + c] = Mt[r * 4 + c]; Rs[r * 3 + c] = Ms[r * 4 + c]; }
     pt[r] = Mt[r * 4 + 3];
     ps[r] = Ms[r * 4 + 3];
   }
-  mul3(Rt, Rs, R);                                   // rotation of s2t
-  for (int r = 0; r < 3; ++r)                        // translation of s2t = R_t^T (p_s - p_t)
-    tr[r] = Rt[r * 3] * (ps[0] - pt[0]) + Rt[r * 3 + 1] * (ps[1] - pt[1]) + Rt[r * 3 + 2] * (ps[2] - pt[2]);
+  inv3(At, Ati);
+  mul3(Ati, Rs, R);                                  // linear part of s2t
+  for (int r = 0; r < 3; ++r)                        // translation of s2t = A_t^-1 (p_s - p_t)
+    tr[r] = Ati[r * 3] * (ps[0] - pt[0]) + Ati[r * 3 + 1] * (ps[1] - pt[1]) + Ati[r * 3 + 2] * (ps[2] - pt[2]);
   double te[3];                                      // t_ess = -R^T t
   for (int r = 0; r < 3; ++r) te[r] = -(R[r] * tr[0] + R[3 + r] * tr[1] + R[6 + r] * tr[2]);
   const double X[9] = {0.0, -te[2], te[1], te[2], 0.0, -te[0], -te[1], te[0], 0.0};
@@ -51,7 +53,51 @@ __global__ void pairwise_fundamental_kernel(const double* __restrict__ c2w, cons
   for (int i = 0; i < 9; ++i) F[(size_t)s * 9 + i] = (float)Fm[i];
 }
 
+// Pluecker ray embedding of the CameraCtrl pose encoder input: ray_condition of the reference
+// (animatediff/data/dataset_validation.py:102-144) for V cameras at H x W, written channel-major [V, 6, H, W] (the layout
+// the dataset hands on after its .permute(0, 3, 1, 2), :256-257) or pixel-major [V, H, W, 6] (ray_condition's own).
+// One thread per (camera, pixel); fp32 like the reference (its c2w / intrinsics are float tensors).
+//   d = normalize((i + .5 - cx) / fx, (j + .5 - cy) / fy, 1);  rays_d = R d;  o = c2w[:3, 3];  out = (o x rays_d, rays_d)
+__global__ void plucker_kernel(const float* __restrict__ K4, const float* __restrict__ c2w, const unsigned char* __restrict__ flip,
+                               float* __restrict__ out, int V, int H, int W, int channel_major) {
+  const int HW = H * W;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)V * HW) return;
+  const int v = (int)(idx / HW), pix = (int)(idx % HW);
+  const int jj = pix / W;
+  int ii = pix % W;
+  if (flip != nullptr && flip[v]) ii = W - 1 - ii;     // horizontally flipped grid (:117-126)
+  const float fx = K4[v * 4], fy = K4[v * 4 + 1], cx = K4[v * 4 + 2], cy = K4[v * 4 + 3];
+  const float xs = ((float)ii + 0.5f - cx) / fx, ys = ((float)jj + 0.5f - cy) / fy;
+  const float nrm = sqrtf(xs * xs + ys * ys + 1.0f);
+  const float dx = xs / nrm, dy = ys / nrm, dz = 1.0f / nrm;
+  const float* M = c2w + (size_t)v * 16;
+  const float rx = M[0] * dx + M[1] * dy + M[2] * dz;
+  const float ry = M[4] * dx + M[5] * dy + M[6] * dz;
+  const float rz = M[8] * dx + M[9] * dy + M[10] * dz;
+  const float ox = M[3], oy = M[7], oz = M[11];
+  const float val[6] = {oy * rz - oz * ry, oz * rx - ox * rz, ox * ry - oy * rx, rx, ry, rz};
+  if (channel_major) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[((size_t)v * 6 + c) * HW + pix] = val[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) out[((size_t)v * HW + pix) * 6 + c] = val[c];
+  }
+}
+
 }  // namespace cvd
+
+extern "C" int cvd_plucker_embedding(const float* intrinsics, const float* c2w, const unsigned char* flip_flag, float* out,
+                                     int views, int H, int W, int channel_major, cvd_stream_t stream) {
+  CVD_REQUIRE(intrinsics && c2w && out, "cvd_plucker_embedding: null pointer");
+  CVD_REQUIRE(views > 0 && H > 0 && W > 0, "cvd_plucker_embedding: views=%d H=%d W=%d", views, H, W);
+  const long long total = (long long)views * H * W;
+  cvd::plucker_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(intrinsics, c2w, flip_flag, out, views,
+                                                                                       H, W, channel_major);
+  CVD_LAUNCH_CHECK("plucker_kernel");
+  return CVD_OK;
+}
 
 extern "C" int cvd_pairwise_fundamental(const double* c2w, const double* K, const int* partner, float* F_mats, int rows,
                                         cvd_stream_t stream) {

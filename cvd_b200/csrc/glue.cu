@@ -545,11 +545,7 @@ static int launch_groupnorm_fused(const float* x, const float* gamma, const floa
   constexpr int PX = 32 * PPL;
   const int csize = HW / PX;
   const size_t smem = (size_t)(kFusedCB * (PX + 1) + 4 * kFusedCB + 16) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    CVD_CUDA(cudaFuncSetAttribute(groupnorm_tokens_fused_kernel<PPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  CVD_CUDA(ensure_dynamic_smem((const void*)groupnorm_tokens_fused_kernel<PPL>, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * F * (C / kFusedCB) * csize));
   cfg.blockDim = dim3(256);
@@ -648,11 +644,7 @@ extern "C" int cvd_tokens_to_video_fwd(const void* tok, const float* bias, const
   if (io_dtype == CVD_DTYPE_F32 && C % 64 == 0 && HW % kTileP == 0 && (long long)B * F * (HW / kTileP) >= 2048 &&
       (((uintptr_t)tok) & 15) == 0) {
     const size_t smem = (size_t)kTileP * (C / 2 + 1) * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (smem > configured) {
-      CVD_CUDA(cudaFuncSetAttribute(tokens_to_video_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    CVD_CUDA(ensure_dynamic_smem((const void*)tokens_to_video_rows_kernel, smem));
     tokens_to_video_rows_kernel<<<(unsigned)(B * F * (HW / kTileP)), 256, smem, st>>>(t, bias, (const float*)residual, (float*)out,
                                                                                   C, F, HW, layout);
     CVD_LAUNCH_CHECK("tokens_to_video_rows_kernel");

@@ -248,11 +248,7 @@ static int launch16(const void* q, const void* k, const void* v, void* out, int 
   const int warps = heads < 8 ? heads : 8;
   const size_t smem = (size_t)3 * 16 * (C + 8) * sizeof(__nv_bfloat16);
   CVD_REQUIRE(smem <= 227 * 1024, "cvd_temporal_attn_fwd: C=%d needs %zu bytes of shared memory", C, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CVD_CUDA(cudaFuncSetAttribute(temporal_attn16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  CVD_CUDA(ensure_dynamic_smem((const void*)temporal_attn16_kernel<D>, smem));
   temporal_attn16_kernel<D><<<T, warps * 32, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                                          (const __nv_bfloat16*)v, (__nv_bfloat16*)out, heads);
   CVD_LAUNCH_CHECK("temporal_attn16_kernel");
@@ -277,11 +273,7 @@ extern "C" int cvd_temporal_attn_fwd(const void* q, const void* k, const void* v
   const int warps = heads < 8 ? heads : 8;
   const size_t smem = (size_t)3 * F * (C + 2) * sizeof(__nv_bfloat16) + (size_t)warps * F * (F + 1) * sizeof(float);
   CVD_REQUIRE(smem <= 227 * 1024, "cvd_temporal_attn_fwd: F=%d C=%d needs %zu bytes of shared memory", F, C, smem);
-  static size_t configured_smem = 0;   // grow-only; one process per GPU
-  if (smem > configured_smem) {
-    CVD_CUDA(cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_smem = smem;
-  }
+  CVD_CUDA(ensure_dynamic_smem((const void*)temporal_attn_kernel, smem));
   temporal_attn_kernel<<<T, warps * 32, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, F, heads, head_dim);
   CVD_LAUNCH_CHECK("temporal_attn_kernel");

@@ -9,7 +9,9 @@ arguments, forward signatures, return values and ``state_dict`` keys, so
 What differs is the execution: every stage runs in hand-written CUDA for sm_100a behind the
 C ABI of ``include/cvd_b200.h`` (dense projections go through cuBLAS via ``F.linear``).
 The dense epipolar mask is never materialised; the fused tcgen05 kernel rebuilds it from a
-12-float-per-row table.  Forward only (inference); there is no CPU path and no fallback.
+12-float-per-row table.  Inference runs entirely on those kernels; under autograd (``train()`` mode or inputs that
+require grad) the ``*_train`` twins record torch glue around the CUDA attention
+forward / backward pair.  There is no CPU path and no fallback.
 """
 import math
 from typing import Any, Dict
@@ -68,12 +70,12 @@ def _wants_grad(module, *tensors):
 
 
 def _require_inference(module, *tensors):
-    """Forward only: refuse to run where autograd would expect a graph."""
+    """The inference-only entry points (the processor called directly) refuse to run where autograd would expect a
+    graph; the layers route such calls to their ``*_train`` twins before they get here."""
     if torch.is_grad_enabled() and (module.training or any(t is not None and t.requires_grad for t in tensors)):
         raise NotImplementedError(
-            "cvd_b200 implements the forward (inference) path only; the backward kernels are "
-            "SURVEY.md section 8(f3).  Call under torch.no_grad() (or put the module in eval() mode "
-            "with inputs that do not require grad).")
+            "EpiAttnProcessor.forward is the inference path; under autograd call the layer (EpiSelfAttention / "
+            "EpiModule), which records the differentiable path (attend_train / forward_train).")
 
 
 class GEGLU(nn.Module):
@@ -198,13 +200,15 @@ class EpiAttnProcessor(nn.Module):
         if host is not None:
             if host.min() < 0 or host.max() >= R_src:
                 raise IndexError("kv_index out of range")
-            if len(self._idx) > 64:
-                self._idx.clear()
+            # never evicted: a captured CUDA graph keeps replaying the ADDRESS of the index tensor it was recorded
+            # with (one graph per pairing when kv_index is a numpy array), so freeing an entry would let replays read
+            # recycled memory.  An entry is R int32 values; V = 8 views have 105 pairings.
             self._idx[key] = idx
         return idx
 
     def forward(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, kv_index=None, temb=None,
-                scale=None, mono_direction=False, fix_firstframe=False, epi_rowp=None, partner=None, **useless_kwargs):
+                scale=None, mono_direction=False, fix_firstframe=False, epi_rowp=None, partner=None, ff_group=None,
+                **useless_kwargs):
         assert hidden_states.ndim == 3   # BF x HW x C  (attention_processor.py:565)
         if mono_direction:
             raise ValueError("kv_index may have bug here. Not supported")   # attention_processor.py:621-622
@@ -241,10 +245,13 @@ class EpiAttnProcessor(nn.Module):
             k_src, vt_src = self.shard.gather_rows(k), self.shard.gather_rows(vt)
         o = ops.epi_attn_fwd(q, k_src, vt_src, epi_rowp, partner, H, attn.F_mat_size)
         if fix_firstframe:
-            # attention_processor.py:629-635: first-frame rows take the batch-mean self value
-            v_self = F.linear(x, w.bf16("v", attn.to_v.weight)).view(-1, 2, FRAMES_PER_VIDEO, N, C)
-            ff = v_self[:, :, 0].float().mean(dim=0, keepdim=True).to(o.dtype)
-            o.view(-1, 2, FRAMES_PER_VIDEO, N, C)[:, :, 0] = ff
+            # attention_processor.py:629-635: first-frame rows take the batch-mean self value; the mean runs over the
+            # rows of ONE processor call, i.e. per chunk of `ff_group` rows in the reference's memory-relief branch
+            # (epi_module.py:436-447)
+            G = R if ff_group is None else ff_group
+            v_self = F.linear(x, w.bf16("v", attn.to_v.weight)).view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)
+            ff = v_self[:, :, :, 0].float().mean(dim=1, keepdim=True).to(o.dtype)
+            o.view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)[:, :, :, 0] = ff
         y = F.linear(o, w.bf16("o", attn.to_out[0].weight))     # bias / rescale are applied by the caller
         return y, _Aux(q, k_src, partner)
 
@@ -330,13 +337,19 @@ class EpiSelfAttention(nn.Module):
             chunk = 128 * 1024 // max(1024, N * n_partners)
             keep = (R // chunk) * chunk
             if kv_index is None:
-                src = torch.arange(R, device=hidden_states.device, dtype=torch.int32)
+                # every row attends to ITSELF; with view sharding the K / V buffers are addressed by GLOBAL rows
+                shard = self.processor.shard
+                first = 0 if shard is None else shard.rank * R
+                src = torch.arange(first, first + R, device=hidden_states.device, dtype=torch.int32)
             else:
                 src = self.processor.partner_index(R, kv_index, hidden_states.device)
             if src.shape[0] != R:
                 raise IndexError("the reference's chunk branch indexes one partner per row")
+            if self.epi_fix_firstframe and keep != R:
+                raise RuntimeError("epi_fix_firstframe with dropped remainder rows: the reference fails here too")
             y, _ = self.processor(self, hidden_states, kv_index=None, scale=scale, mono_direction=self.epi_mono_direction,
-                                  fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp[:R].contiguous(), partner=src, **kw)
+                                  fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp[:R].contiguous(), partner=src,
+                                  ff_group=chunk, **kw)
             return y[:keep], None
         return self.processor(self, hidden_states, kv_index=kv_index, scale=scale, mono_direction=self.epi_mono_direction,
                               fix_firstframe=self.epi_fix_firstframe, epi_rowp=rowp, **kw)

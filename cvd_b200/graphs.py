@@ -12,6 +12,11 @@ Semantics are unchanged, including the global-RNG draw of the first-frame slope 
 the default CUDA generator with the graph, so every replay consumes fresh Philox offsets).  The
 returned tensors are the graph's static outputs: consume (or clone) them before the next call
 with the same signature.
+
+A captured graph replays the ADDRESSES it was recorded with, including the bf16 copies the modules keep of their
+parameters (``_WeightCache``).  Those copies are rebuilt when a parameter is modified (``load_state_dict``, an optimizer
+step), so every call compares the parameters' version counters with the ones seen at capture time and drops all graphs
+when they differ (``invalidate()`` does the same by hand).
 """
 import numpy as np
 import torch
@@ -56,8 +61,21 @@ class GraphedModule(torch.nn.Module):
         self.module = module
         self.warmup = warmup
         self._graphs = {}
+        self._stamp = None
+
+    def _param_stamp(self):
+        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    def invalidate(self):
+        """Forget every captured graph (their static buffers are released with them)."""
+        self._graphs.clear()
+        self._stamp = None
 
     def forward(self, *args, **kwargs):
+        stamp = self._param_stamp()
+        if stamp != self._stamp:
+            self._graphs.clear()
+            self._stamp = stamp
         key = (_sig(args), _sig(kwargs))
         entry = self._graphs.get(key)
         if entry is None:

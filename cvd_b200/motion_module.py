@@ -8,7 +8,10 @@ TemporalSelfAttention :484) and the two processors the shipped config installs o
 (``animatediff/models/attention_processor.py``: ``PoseAdaptorAttnProcessor`` :228-371 on
 ``attention_blocks.0``, ``AttnProcessor(attn_type="temporal")`` :17-110 on ``attention_blocks.1``;
 ``configs/inference_config.yaml:48-56``).  Same names, signatures and ``state_dict`` keys.
-Forward only; causal-mask variants (unused by the config) are not built.
+Inference runs on the CUDA kernels of ``libcvd_b200.so``.  Under autograd (``train()`` mode or inputs that require
+grad -- the reference's training script keeps these modules frozen but still back-propagates THROUGH them into the epi
+modules below, train_epi_control.py:589-630) ``forward_train`` records the same arithmetic as torch ops (bf16 GEMM
+operands, fp32 residual stream, SDPA over the 16 frames).  Causal-mask variants (unused by the config) are not built.
 """
 import math
 from typing import Any, Dict
@@ -18,7 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib, ops
-from .epi_module import FeedForward, _require_inference, _WeightCache, zero_module
+from .epi_module import FeedForward, _wants_grad, _WeightCache, zero_module
 
 
 def get_motion_module(in_channels, motion_module_type: str, motion_module_kwargs: dict):
@@ -119,6 +122,23 @@ class TemporalSelfAttention(nn.Module):
         o = ops.temporal_attn(q, k, v, self.heads)
         return F.linear(o, w.bf16("o", self.to_out[0].weight))
 
+    def attend_train(self, n, pose_tokens=None, scale=None):
+        """Autograd twin of :meth:`attend` + the to_out bias / rescale: n bf16 [T, F, C] -> fp32 [T, F, C]."""
+        bf = torch.bfloat16
+        proc = self.processor
+        if isinstance(proc, PoseAdaptorAttnProcessor) and pose_tokens is not None:
+            m = F.linear(n + pose_tokens, proc.qkv_merge.weight.to(bf), proc.qkv_merge.bias.to(bf))
+            n = m * (scale or proc.scale) + n
+        T, Fr, C = n.shape
+        H = self.heads
+
+        def heads(t):
+            return t.view(T, Fr, H, C // H).transpose(1, 2)
+        q, k, v = (heads(F.linear(n, p.weight.to(bf))) for p in (self.to_q, self.to_k, self.to_v))
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(T, Fr, C)
+        y = F.linear(o, self.to_out[0].weight.to(bf)).float() + self.to_out[0].bias.float()
+        return y / self.rescale_output_factor
+
 
 class TemporalTransformerBlock(nn.Module):
     """motion_module.py:397-460."""
@@ -162,6 +182,21 @@ class TemporalTransformerBlock(nn.Module):
         hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
         return hs, hb
 
+    def forward_train(self, hs, pose_tokens=None, scale=None):
+        """Autograd twin of :meth:`forward_stream` (motion_module.py:447-460): fp32 stream [T, F, C] in, out."""
+        bf = torch.bfloat16
+        C = hs.shape[-1]
+        frames = hs.shape[1]
+        for attn, norm in zip(self.attention_blocks, self.norms):
+            n = F.layer_norm(hs, (C,), norm.weight.float(), norm.bias.float(), norm.eps)
+            if attn.pos_encoder is not None:
+                n = n + attn.pos_encoder.pe[0, :frames].to(device=hs.device, dtype=torch.float32)
+            hs = hs + attn.attend_train(n.to(bf), pose_tokens, scale)
+        n = F.layer_norm(hs, (C,), self.ff_norm.weight.float(), self.ff_norm.bias.float(), self.ff_norm.eps).to(bf)
+        proj, out = self.ff.net[0].proj, self.ff.net[2]
+        hcol, gate = F.linear(n, proj.weight.to(bf), proj.bias.to(bf)).chunk(2, dim=-1)
+        return hs + F.linear(hcol * F.gelu(gate), out.weight.to(bf)).float() + out.bias.float()
+
 
 class TemporalTransformer3DModel(nn.Module):
     """motion_module.py:253-394."""
@@ -199,7 +234,6 @@ class TemporalTransformer3DModel(nn.Module):
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None,
                 cross_attention_kwargs: Dict[str, Any] = {}):
         assert hidden_states.dim() == 5, f"Expected hidden_states to have ndim=5, but got ndim={hidden_states.dim()}."
-        _require_inference(self, hidden_states)
         if attention_mask is not None:
             raise _lib.CvdError("temporal attention masks are not supported (the reference passes None)")
         x = hidden_states.contiguous()
@@ -209,6 +243,8 @@ class TemporalTransformer3DModel(nn.Module):
         scale = cross_attention_kwargs.get("scale", None)
         if pose is not None and pose.ndim != 5:
             raise _lib.CvdError("pose_feature must be in video layout [B,C,F,h,w]")
+        if _wants_grad(self, hidden_states, pose):
+            return self.forward_train(x, pose, scale)
         g = ops.groupnorm_tokens(x, w.f32("gn_w", self.norm.weight), w.f32("gn_b", self.norm.bias), self.norm.num_groups,
                                  self.norm.eps, _lib.LAYOUT_BHW_F)
         # fp32 residual stream straight out of the proj_in GEMM; its bias lands in the first fused residual + LayerNorm
@@ -224,6 +260,28 @@ class TemporalTransformer3DModel(nn.Module):
             hb = hs.to(torch.bfloat16)
         t = F.linear(hb, w.bf16("out_w", self.proj_out.weight))
         return ops.tokens_to_video(t, w.f32("out_b", self.proj_out.bias), x, _lib.LAYOUT_BHW_F)
+
+    def forward_train(self, x, pose=None, scale=None):
+        """Autograd-recorded twin of :meth:`forward` (motion_module.py:370-394): per-frame GroupNorm, ``b c f h w ->
+        (b h w) f c``, proj_in, blocks, proj_out, inverse layout, residual.  The training script freezes this module
+        but the gradients of the epi modules in front of it flow through here (train_epi_control.py:589-630)."""
+        if not x.is_cuda:
+            raise _lib.CvdError("cvd_b200 has no CPU path: hidden_states must be a CUDA tensor")
+        bf = torch.bfloat16
+        B, C, Fr, h, w_ = x.shape
+
+        def tokens(v):      # [B,C,F,h,w] -> [(b h w), F, C]
+            return v.permute(0, 3, 4, 2, 1).reshape(B * h * w_, Fr, C)
+        xt = x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w_)
+        g = F.group_norm(xt.float(), self.norm.num_groups, self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
+        tok = tokens(g.view(B, Fr, C, h, w_).permute(0, 2, 1, 3, 4)).to(bf)
+        hs = F.linear(tok, self.proj_in.weight.to(bf)).float() + self.proj_in.bias.float()
+        pose_tok = None if pose is None else tokens(pose).to(bf)
+        for block in self.transformer_blocks:
+            hs = block.forward_train(hs, pose_tok, scale)
+        t = F.linear(hs.to(bf), self.proj_out.weight.to(bf)).float() + self.proj_out.bias.float()
+        out = t.view(B, h, w_, Fr, C).permute(0, 4, 3, 1, 2) + x.float()
+        return out.to(x.dtype)
 
 
 class VanillaTemporalModule(nn.Module):

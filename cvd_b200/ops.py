@@ -289,3 +289,18 @@ def pairwise_fundamental(c2w, K, partner):
               _check(partner, torch.int32, "partner"), F_mats.data_ptr(), rows, _stream())
     _count()
     return F_mats
+
+
+def plucker_embedding(intrinsics, c2w, H, W, flip_flag=None, channel_major=True):
+    """Device version of ``ray_condition`` (dataset_validation.py:102-144): intrinsics fp32 [V,4] (fx, fy, cx, cy),
+    c2w fp32 [V,4,4] -> fp32 [V,6,H,W] (``channel_major``, the dataset's layout) or [V,H,W,6] (ray_condition's)."""
+    V = c2w.shape[0]
+    out = torch.empty((V, 6, H, W) if channel_major else (V, H, W, 6), device=c2w.device, dtype=torch.float32)
+    fp = None
+    if flip_flag is not None:
+        flip_flag = flip_flag.to(device=c2w.device, dtype=torch.uint8).contiguous()
+        fp = _check(flip_flag, torch.uint8, "flip_flag")
+    _lib.call("cvd_plucker_embedding", _check(intrinsics, torch.float32, "intrinsics"), _check(c2w, torch.float32, "c2w"),
+              fp, out.data_ptr(), V, H, W, 1 if channel_major else 0, _stream())
+    _count()
+    return out

@@ -90,11 +90,6 @@ int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const f
                            int heads, int head_dim, int n_partners, int feat, float F_mat_size,
                            cvd_stream_t stream);
 
-/* Profiling aid: with CVD_ATTN_PP=1 and CVD_ATTN_PP_PROF=1 in the environment the opt-in ping-pong variant of the
- * d=40 kernel records per-CTA cycle counters (softmax-side s_full waits, issuer-side waits and issue phases); this
- * prints their means for the last such launch to stderr.  No effect on results. */
-int cvd_epi_attn_pp_profile_dump(void);
-
 /* ---- f3 (first CUDA path): forward with the statistic the backward needs, and the backward of the attention core.
  *      Replaces autograd through EpiAttnProcessor (attention_processor.py:573-619) in train_epi_control.py:512-642; the
  *      epipolar bias has no gradient (epi_module.py:329,393).
@@ -174,9 +169,18 @@ int cvd_scale_add_fwd(const void* a, const void* b, float scale, void* out, long
  *      V-view sampler runs on the CPU before every UNet call
  *      (pipelines/pipeline_animation_epi_advanced.py:636-647 -> data/dataset_validation.py:28-64):
  *        F[s] = K[t]^-T E(inv(c2w[t]) c2w[s]) K[s]^-1,  t = partner[s]
- *      c2w fp64 [rows,4,4] (rigid poses), K fp64 [rows,3,3], partner int32 [rows], F_mats fp32 [rows,3,3]. */
+ *      c2w fp64 [rows,4,4] (any affine pose: bottom row 0 0 0 1; inverted like np.linalg.inv), K fp64 [rows,3,3], partner int32 [rows], F_mats fp32 [rows,3,3]. */
 int cvd_pairwise_fundamental(const double* c2w, const double* K, const int* partner, float* F_mats,
                              int rows, cvd_stream_t stream);
+
+/* ---- f2, second half: Pluecker ray embedding of the pose encoder input, replacing ray_condition
+ *      (data/dataset_validation.py:102-144; data/dataset_train_realestate10k.py:168-210) on the CPU.
+ *      intrinsics fp32 [views,4] = (fx, fy, cx, cy) in pixels of the H x W grid; c2w fp32 [views,4,4];
+ *      flip_flag uint8 [views] or NULL (horizontally mirrored pixel grid, :117-126);
+ *      out fp32 [views,6,H,W] (channel_major != 0: what the dataset passes on after .permute(0,3,1,2)) or
+ *      [views,H,W,6] (ray_condition's own layout): (o x d, d) with d the world-space unit ray through the pixel centre. */
+int cvd_plucker_embedding(const float* intrinsics, const float* c2w, const unsigned char* flip_flag, float* out,
+                          int views, int H, int W, int channel_major, cvd_stream_t stream);
 
 /* ---- multi-GPU view sharding (new; the reference has no multi-GPU inference): pull the rows this
  *      rank's queries attend to out of the peers' memory over NVLink.

@@ -114,6 +114,33 @@ def pairwise_F_mats(c2w, K, partner, n_frames=FRAMES_PER_VIDEO):
 
 
 # ----------------------------------------------------------------------------------------
+# f2  Pluecker ray embedding          animatediff/data/dataset_validation.py:102-144
+# ----------------------------------------------------------------------------------------
+def plucker_embedding(intrinsics, c2w, H, W, flip_flag=None):
+    """ray_condition (dataset_validation.py:102-144) for V cameras: intrinsics [V,4] = (fx, fy, cx, cy), c2w [V,4,4]
+    -> fp32 [V,H,W,6] = (o x d, d), d = the world-space unit ray through each pixel centre (i + .5, j + .5);
+    ``flip_flag`` [V] bool mirrors the pixel grid of those cameras horizontally (:117-126)."""
+    K = np.asarray(intrinsics, dtype=np.float32)
+    M = np.asarray(c2w, dtype=np.float32)
+    V = M.shape[0]
+    jj, ii = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    i = np.broadcast_to(ii.reshape(1, H * W), (V, H * W)).copy()
+    if flip_flag is not None:
+        flip = np.asarray(flip_flag, dtype=bool)
+        i[flip] = (W - 1) - i[flip]
+    i = i + np.float32(0.5)
+    j = np.broadcast_to(jj.reshape(1, H * W), (V, H * W)) + np.float32(0.5)
+    xs = (i - K[:, 2:3]) / K[:, 0:1]
+    ys = (j - K[:, 3:4]) / K[:, 1:2]
+    d = np.stack([xs, ys, np.ones_like(xs)], axis=-1)
+    d = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    rays_d = d @ np.swapaxes(M[:, :3, :3], -1, -2)
+    rays_o = np.broadcast_to(M[:, None, :3, 3], rays_d.shape)
+    out = np.concatenate([np.cross(rays_o, rays_d), rays_d], axis=-1)
+    return torch.from_numpy(out.reshape(V, H, W, 6).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------------------
 # a1/a2  epipolar additive bias            animatediff/models/epi_module.py:293-346,398-407
 # ----------------------------------------------------------------------------------------
 def pixel_centres(feat, S):

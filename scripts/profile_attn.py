@@ -55,6 +55,3 @@ else:
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print(f"feat={feat} C={C} R={R}: {ms * 1e3:.1f} us/launch, {4.0 * R * N * N * C / ms / 1e9:.1f} TFLOP/s")
-if os.environ.get("CVD_ATTN_PP_PROF"):
-    sys.stderr.flush()
-    _lib.load().cvd_epi_attn_pp_profile_dump()

@@ -220,10 +220,34 @@ def sampler():
     save("sampler", **out)
 
 
+def plucker():
+    """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
+    256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
+    from animatediff.data.dataset_validation import ray_condition
+    ds = ValRealEstate10KPoseFolded(sample_n_frames=16, relative_pose=True, sample_size=256, validation_prompts=["x"],
+                                    pose_file_0=os.path.join(REF, gi.POSE_FILE_0),
+                                    pose_file_1=os.path.join(REF, gi.POSE_FILE_1))
+    c2w_list, _K, intr_list = ds.load_cameras_specific()
+    intr = torch.as_tensor(np.array(intr_list)).float()[None]            # [1, 31, 4], as get_batch builds it (:253)
+    c2w = torch.as_tensor(c2w_list)[None]                                # [1, 31, 4, 4] float32
+    full = ray_condition(intr, c2w, 256, 256, device="cpu")[0].permute(0, 3, 1, 2)   # [31, 6, 256, 256]
+    small_K = torch.tensor([[[6.1, 4.3, 3.4, 2.6]] * 4])
+    small = ray_condition(small_K, c2w[:, :4], 5, 7, device="cpu")[0]                 # [4, 5, 7, 6]
+    flip = torch.tensor([False, True, False, True])
+    flipped = ray_condition(small_K, c2w[:, :4], 5, 7, device="cpu", flip_flag=flip)[0]
+    save("plucker", intrinsics=intr[0], c2w=c2w[0], frame17=full[17], sub8=full[:, :, 3::8, 5::8],
+         chan_sum=full.double().sum(dim=(2, 3)), abs_sum=full.double().abs().sum().item(),
+         small_K=small_K[0], small=small, flipped=flipped, flip=flip)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "plucker":
+        plucker()
+        sys.exit(0)
     Fm = geometry()
     bias(Fm)
     attention(Fm)
     module(Fm)
     temporal()
     sampler()
+    plucker()

@@ -2,7 +2,7 @@
 (symmetric-memory buffer passed as k / vt: TMA over NVLink at 8x8, plain loads at 4x4) give bit-identical results to the
 same call on a local copy of those rows."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np, torch, torch.distributed as dist
 import golden_inputs as gi
@@ -11,7 +11,7 @@ from cvd_b200 import _lib, ops, sharding
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 assert world == 2
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"])); dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=dev)
 shard = sharding.ViewShard(); peer = sharding.PeerExchange(shard)
 R, H = 64, 8

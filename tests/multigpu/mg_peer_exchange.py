@@ -1,7 +1,7 @@
 """2-GPU check of the NVLink peer exchange (run under torchrun, 2 ranks): the sharded layer output of each
 rank equals the corresponding rows of the un-sharded layer computed on one GPU."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 import numpy as np, torch, torch.distributed as dist
 import cvd_b200, golden_inputs as gi
@@ -9,7 +9,7 @@ from cvd_b200 import sharding
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ["LOCAL_RANK"])); dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=dev)
 shard = sharding.ViewShard(); peer = sharding.PeerExchange(shard)
 C, feat, Rg = 320, 16, 64 * world // 2 * 2 // 2 * 1   # 64 rows total for world=2 (32 per rank)

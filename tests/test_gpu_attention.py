@@ -163,36 +163,18 @@ def test_unsupported_shape_is_an_error(dev):
         ops.epi_attn_fwd(q, q, vt, None, partner, 8, 256.0)
 
 
-def test_two_warpgroup_variant_forced(dev):
-    """The d = 40 two-warpgroup kernel serves feat >= 64 by default; CVD_ATTN_WG2=1 forces it at 32x32 and 16x16 too.
-    The switch is read once per process, so the parity cases are re-run in a child process with it set."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("CVD_ATTN_WG2_CHILD") == "1":
-        pytest.skip("already inside the forced-variant child")
-    env = dict(os.environ, CVD_ATTN_WG2="1", CVD_ATTN_WG2_CHILD="1")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_attention.py"), "-m", "gpu",
-                          "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
-                         capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-
-
-@pytest.mark.parametrize("switch", ["CVD_ATTN_PP", "CVD_ATTN_CS"])
-def test_opt_in_variants_forced(dev, switch):
-    """The d = 40 ping-pong kernel (two query tiles per CTA, every softmax warp alternating between two chains) and the
-    column-split kernel (two warpgroups share each score tile, reference maximum agreed through shared memory) are
-    opt-in A/B variants (measured slower than the default: profiles/); they must still be exact."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("CVD_ATTN_WG2_CHILD") == "1":
-        pytest.skip("already inside a forced-variant child")
-    env = dict(os.environ, CVD_ATTN_WG2_CHILD="1")
-    env[switch] = "1"
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_attention.py"), "-m", "gpu",
-                          "-q", "-x", "-k", "tcgen05 or properties"], env=env, cwd=root,
-                         capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+@pytest.mark.parametrize("theta", [None, 0.9])
+def test_tcgen05_kernel_vs_oracle_bias_directly(golden, dev, theta):
+    """The in-kernel bias against the ORACLE's dense bias with no product code in between: oracle.epi_bias (pinned to
+    the reference's get_attn_map by tests/test_oracle_golden.py) -> fp32 softmax(q k^T / sqrt(d) + bias) v on the device
+    -> the tcgen05 kernel, at the bench shape's latent (32x32, d = 40), both first-frame rules."""
+    from cvd_b200 import ops
+    from oracle import epi_oracle as O
+    import golden_inputs as gi
+    R, feat, d = 32, 32, 40
+    q, k, v, vt, rowp, _bias_prod, partner = make_case(dev, R, feat, 8, d, 77, golden, theta=theta)
+    Fm = gi.tile_F(t(golden["geometry"]["F_mats"]), R)
+    bias = O.epi_bias(Fm, feat, 256, theta=theta)                      # CPU oracle, [R,N,N] fp32
+    bias = torch.nan_to_num(bias, nan=0.0, posinf=0.0, neginf=0.0).to(dev)
+    out = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
+    assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=REL_TC, max_abs=0.08, what="tcgen05 vs oracle bias")

@@ -76,3 +76,35 @@ def test_lse_matches_dense_logits(dev):
         logits = torch.matmul(qh, kh.transpose(-1, -2)) * d ** -0.5 + bias[:, None]
         ref = torch.logsumexp(logits, dim=-1) * 1.4426950408889634
         assert float((lse - ref).abs().max()) < 2e-2, (feat, d, float((lse - ref).abs().max()))
+
+
+def test_attention_forward_backward_config5_shape(dev):
+    """BASELINE config 5 (train_epi_control.py:589-630: 8 two-view pairs per GPU -> R = 256 rows, 32x32 latent, d = 40).
+    R > 200 takes the reference's memory-relief branch (epi_module.py:424-451): with a tensor F_mats every row attends
+    to ITSELF, so partner = arange(R).  Reference: fp32 autograd through the dense restatement, 32 rows at a time
+    (rows are independent for a fixed partner map)."""
+    from cvd_b200 import _lib, ops
+    R, feat, d, H = 256, 32, 40, 8
+    N, C = feat * feat, H * d
+    g = torch.Generator().manual_seed(555)
+    q, k, v, d_out = (torch.randn(R, N, C, generator=g).to(dev).to(torch.bfloat16) for _ in range(4))
+    Fm = gi.tile_F(t(np.load(os.path.join(ROOT, "tests", "golden", "geometry.npz"))["F_mats"]), R).to(dev)
+    partner = torch.arange(R, device=dev, dtype=torch.int32)
+    rowp = ops.epi_row_params(Fm, feat, 256.0, None, _lib.FF_HORIZONTAL)
+    qp, kp, vp = (a.clone().requires_grad_(True) for a in (q, k, v))
+    out = ops.EpiAttnFunction.apply(qp, kp, vp, rowp, partner, H, 256.0)
+    out.backward(d_out)
+    worst = [0.0] * 4
+    ident = torch.arange(32, device=dev, dtype=torch.int32)
+    for lo in range(0, R, 32):
+        sl = slice(lo, lo + 32)
+        bias = ops.epi_bias_dense(rowp[sl].contiguous(), feat, 256.0)
+        qf, kf, vf = (a[sl].float().requires_grad_(True) for a in (q, k, v))
+        ref = attention_ref(qf, kf, vf, H, bias, ident)
+        ref.backward(d_out[sl].float())
+        errs = (rel_l2(out[sl], ref), rel_l2(qp.grad[sl], qf.grad), rel_l2(kp.grad[sl], kf.grad), rel_l2(vp.grad[sl], vf.grad))
+        worst = [max(a, b) for a, b in zip(worst, errs)]
+        del bias, ref, qf, kf, vf
+    print(f"config-5 shape (R=256, 32x32, d=40): worst 32-row chunk rel-L2 out {worst[0]:.2e} dq {worst[1]:.2e} "
+          f"dk {worst[2]:.2e} dv {worst[3]:.2e}")
+    assert worst[0] < 1e-2 and max(worst[1:]) < 2e-2, worst

@@ -196,3 +196,41 @@ def test_multiview_loop_sharded_world2_equals_single_process():
     u = ToyUNet()
     _run_mv(lat.clone(), text, Fm, poses, None, u, 11)
     assert len(u.calls) == 14
+
+
+def test_ddim_schedule_against_independent_fp64_fixture():
+    """DDIMSchedule.step / renoise against tests/golden/ddim.npz: an independent float64 derivation of the published
+    DDIM update (make_ddim_fixture.py) over ALL 25 timesteps of the reference's default run, including the last step
+    whose previous timestep is negative (alpha_prev = 1).  diffusers itself is not available here: this pins the
+    restatement against a second derivation, not against diffusers ("parity unpinned vs diffusers")."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddim.npz"))
+    sch = sampler.DDIMSchedule()
+    ts = sch.set_timesteps(25)
+    assert ts == [int(t) for t in g["timesteps"]]
+    stride = 1000 // 25
+    for i, t in enumerate(ts):
+        a_t = float(sch.alphas_cumprod[t])
+        a_p = float(sch.alphas_cumprod[t - stride]) if t - stride >= 0 else float(sch.final_alpha_cumprod)
+        assert abs(a_t - g["alpha_t"][i]) <= 2e-6 * g["alpha_t"][i] + 1e-9
+        assert abs(a_p - g["alpha_prev"][i]) <= 2e-6 * g["alpha_prev"][i] + 1e-9
+    assert g["alpha_prev"][-1] == 1.0
+    # single steps from the fixture's own states (no error accumulation): fp32 tables vs the fp64 derivation
+    x_in = np.concatenate([g["x0"][None], g["traj"][:-1]], axis=0)
+    for i, t in enumerate(ts):
+        out = sch.step(torch.from_numpy(g["eps"][i]).float(), t, torch.from_numpy(x_in[i]).float())
+        ref = torch.from_numpy(g["traj"][i]).float()
+        assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max()), (i, t)
+    # whole trajectory in fp64 through the product's update
+    sch64 = sampler.DDIMSchedule()
+    sch64.set_timesteps(25)
+    sch64.alphas_cumprod = torch.cumprod(1.0 - torch.linspace(0.00085, 0.012, 1000, dtype=torch.float64), dim=0)
+    sch64.final_alpha_cumprod = torch.tensor(1.0, dtype=torch.float64)
+    x = torch.from_numpy(g["x0"])
+    for i, t in enumerate(ts):
+        x = sch64.step(torch.from_numpy(g["eps"][i]), t, x)
+    assert float((x - torch.from_numpy(g["traj"][-1])).abs().max()) < 1e-9
+    for j, t in enumerate(g["renoise_t"]):
+        out = sch.renoise(torch.from_numpy(g["renoise_in"]).float(), int(t), torch.from_numpy(g["renoise_noise"]).float())
+        ref = torch.from_numpy(g["renoise_out"][j]).float()
+        assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
