@@ -24,6 +24,7 @@ SIGNATURES = {
     "cvd_epi_row_params": [_P, _P, _P, _I, _I, _F, _F, _F, _I, _I, _P],
     "cvd_epi_bias_dense": [_P, _P, _I, _I, _F, _P],
     "cvd_epi_attn_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    "cvd_epi_attn_fwd_sharded": [_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_lse": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "cvd_epi_attn_fwd_simt": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],

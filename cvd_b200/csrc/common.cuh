@@ -37,6 +37,17 @@ int fail(int code, const char* fmt, ...);
 
 constexpr int kNumSMs = 148;  // B200
 
+// K / V^T operands of the attention kernels: one buffer, or one buffer per source GPU of a view-sharded run (the peers'
+// symmetric-memory copies through their NVLink mappings).  Partner rows are numbered globally: row p lives in source
+// p / rows_per_src at local row p % rows_per_src.
+constexpr int kMaxKvSrc = 8;
+struct KvSrc {
+  const void* k[kMaxKvSrc];
+  const void* v[kMaxKvSrc];
+  int n_src;
+  int rows_per_src;
+};
+
 // opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (once per kernel and device)
 cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);
 
@@ -88,19 +99,32 @@ __device__ __forceinline__ void store_from_float<__half>(__half* p, size_t i, fl
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+// cluster_x > 1: the grid is launched as thread-block clusters of cluster_x consecutive CTAs (gridDim.x % cluster_x == 0)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      unsigned cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  return launch_pdl_cluster(kernel, grid, block, smem, st, 1u, args...);
 }
 
 }  // namespace cvd

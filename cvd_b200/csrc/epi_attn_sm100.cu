@@ -39,8 +39,8 @@
 
 namespace cvd {
 // csrc/epi_attn_small.cu: warp-level kernel for the N <= 64 grids; -1000 = not a small-grid configuration
-int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out,
-                            float* lse, int R, int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st);
+int epi_attn_small_dispatch(const void* q, const KvSrc& kv, const float* rowp, const int* partner, void* out, float* lse, int R,
+                            int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st);
 namespace sm100 {
 
 using namespace ptx;
@@ -52,9 +52,17 @@ constexpr int kThreads = 160;   // warps 0-3 softmax | warp 4 TMA producer + MMA
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 16.0f;  // lazy rescale: only when a score exceeds the reference by > 2^16
 
-template <int D, int FEAT>
+// CL = CTAs per cluster.  CL > 1 ("multicast"): the CL query tiles of one (row, head) form a thread-block cluster and
+// share every K / V^T tile -- ONE TMA load per tile, issued by CTA (tile % CL), is delivered to the same shared-memory
+// stage of all CL CTAs (cp.async.bulk.tensor ... .multicast::cluster).  When K / V^T live in a PEER GPU's HBM (views
+// sharded across GPUs, the partner view's rows are remote) every byte then crosses NVLink once per (row, head) instead of
+// once per query tile, straight into shared memory, under the softmax of the tiles in front of it: the exchange of the
+// sharded layer is fused into the attention kernel.  A stage is refilled once ALL CL CTAs have consumed it: their MMA
+// commits arrive (multicast) on the stage's "empty" barrier of every CTA, which therefore counts CL arrivals.
+template <int D, int FEAT, int CL = 1>
 struct Cfg {
   static_assert(D % 8 == 0 && (D % 16 == 0 || D % 16 == 8), "head_dim must be a multiple of 8");
+  static_assert(CL >= 1 && CL <= 8 && (CL & (CL - 1)) == 0, "cluster size: 1, 2, 4 or 8");
   static constexpr int kN = FEAT * FEAT;
   static constexpr int kTiles = (kN + kTileN - 1) / kTileN;      // per partner
   static constexpr int kKBlocks = (D + 63) / 64;          // 128-byte swizzle atoms along the head dim
@@ -83,10 +91,14 @@ struct Cfg {
   static constexpr int kTmemCols = (kSplitP || kFour) ? 128 : 256;
   static constexpr int kColP = kAliasP ? kColS : (kSplitP ? 0 : kColO + kDV);   // kSplitP: relative to the 2nd allocation
   static_assert(kColO + kDV <= 256, "TMEM budget");
-  // K/V ring depth (never deeper than the tile count)
+  // K/V ring depth (never deeper than the tile count).  Multicast build: tiles may come over NVLink (~2 us of latency
+  // against a tile period of ~1.3 us per CTA at four CTAs per SM), so K gets a third stage: K_{j+3} is requested when
+  // every CTA of the cluster has finished Q K_j^T and is needed three tile periods later; V_{j+1} is requested when
+  // P V_{j-1} has completed everywhere and is needed two periods later.
   static constexpr int kWant = kFour ? 2 : (D <= 40 ? 3 : (D <= 80 ? 2 : (kTiles > 1 ? 2 : 1)));
-  static constexpr int kKStages = kWant < kTiles ? kWant : kTiles;
-  static constexpr int kVStages = kKStages;
+  static constexpr int kWantK = (CL > 1 && kWant < 3) ? 3 : kWant;
+  static constexpr int kKStages = kWantK < kTiles ? kWantK : kTiles;
+  static constexpr int kVStages = kWant < kTiles ? kWant : kTiles;
   static constexpr int kSmemData = kQBytes + kKStages * kKBytes + kVStages * kVBytes;
   // three-CTA build: d=40 must NOT fit a 4th CTA (4 x 128 TMEM columns would starve the 32-column allocations);
   // four-CTA build: must not fit a 5th (no TMEM left for it)
@@ -101,13 +113,23 @@ struct Barriers {
   uint32_t tmem_base, tmem_p;
 };
 
-template <int D, int FEAT, bool DBG, bool PIPE>
-__global__ void __launch_bounds__(kThreads, Cfg<D, FEAT>::kMinBlocks)
-epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const float* __restrict__ rowp,
-                    const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R, int H, int n_partners,
-                    float step, float* __restrict__ dbg, float* __restrict__ lse) {
-  using C = Cfg<D, FEAT>;
+// K / V^T may be spread over several buffers of equal row count (one per source GPU when the views are sharded: the
+// symmetric-memory copies of the peers, addressed through their NVLink mappings); partner rows are numbered globally,
+// row p lives in buffer p / rows_per_src at local row p % rows_per_src.  A single local buffer is source 0.
+constexpr int kMaxSrc = kMaxKvSrc;
+struct KvMaps {
+  CUtensorMap k[kMaxSrc];
+  CUtensorMap v[kMaxSrc];
+};
+
+template <int D, int FEAT, bool DBG, bool PIPE, int CL>
+__global__ void __launch_bounds__(kThreads, Cfg<D, FEAT, CL>::kMinBlocks)
+epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ KvMaps kv,
+                    const float* __restrict__ rowp, const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, int R,
+                    int H, int n_partners, int rows_per_src, float step, float* __restrict__ dbg, float* __restrict__ lse) {
+  using C = Cfg<D, FEAT, CL>;
+  constexpr uint16_t kMcMask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr int N = C::kN;
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
   constexpr int kRowsPerTile = (kTileN + FEAT - 1) / FEAT;   // key-grid rows touched by one key tile
@@ -130,8 +152,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 4 && lane == 0) {
     prefetch_tmap(&tmQ);
-    prefetch_tmap(&tmK);
-    prefetch_tmap(&tmV);
+    prefetch_tmap(&kv.k[0]);
+    prefetch_tmap(&kv.v[0]);
     mbar_init(smem_u32(&bars->q_full), 1);
     mbar_init(smem_u32(&bars->s_full), 1);
     mbar_init(smem_u32(&bars->s_free), 128);
@@ -140,9 +162,9 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(smem_u32(&bars->o_done), 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(smem_u32(&bars->k_full[i]), 1);
-      mbar_init(smem_u32(&bars->k_empty[i]), 1);
+      mbar_init(smem_u32(&bars->k_empty[i]), CL);      // one (multicast) commit arrival per CTA of the cluster
       mbar_init(smem_u32(&bars->v_full[i]), 1);
-      mbar_init(smem_u32(&bars->v_empty[i]), 1);
+      mbar_init(smem_u32(&bars->v_empty[i]), CL);
     }
     fence_mbar_init();
   }
@@ -153,7 +175,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all();     // no CTA multicasts into (or arrives on) a peer whose barriers are not initialised yet
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   const uint32_t tmemP = C::kSplitP ? bars->tmem_p : tmem + C::kColP;
@@ -176,7 +199,7 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
       for (int kb = 0; kb < C::kKBlocks; ++kb) {
         tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
-        tma_load_3d(sK + kb * kTileN * 128, &tmK, kb * 64, h, partner[r] * N, smem_u32(&bars->q_full));
+        tma_load_3d(sK + kb * kTileN * 128, &kv.k[0], kb * 64, h, partner[r] * N, smem_u32(&bars->q_full));
       }
     }
     __syncwarp();
@@ -196,26 +219,48 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // the loop (waits are warp-wide), one elected lane issues.  Ring stages are refilled by the issuer itself right
     // where their consumer MMA is known to have been issued long ago:
     //   K(j + stages) after Q K_j^T (k_empty), before Q K_{j+1}^T is issued;  V(j - 1 + stages) after P V_{j-1}.
-    auto load_k = [&](int lt) {
+    // Multicast build: every CTA arms its own "full" barrier for the bytes of the tile; the tile itself is fetched by
+    // ONE CTA of the cluster (tile % CL) and delivered to all of them.  `refill` = the stage has been used before: the
+    // fetching CTA first waits until the MMAs that read it have completed in EVERY CTA (CL multicast commit arrivals).
+    auto load_k = [&](int lt, bool refill) {
       const int p = lt / C::kTiles, jt = lt % C::kTiles;
-      const int rr = partner[p * R + r];
+      const int pr = partner[p * R + r];
+      const int src = pr / rows_per_src, rr = pr - src * rows_per_src;
       const int st = lt % C::kKStages;
+      const bool mine = (CL == 1) || ((uint32_t)(lt % CL) == crank);
+      if (refill && mine) mbar_wait(smem_u32(&bars->k_empty[st]), ((lt / C::kKStages) - 1) & 1);
       if (elect_one()) {
         mbar_expect_tx(smem_u32(&bars->k_full[st]), C::kKBytes);
+        if (mine) {
 #pragma unroll
-        for (int kb = 0; kb < C::kKBlocks; ++kb)
-          tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &tmK, kb * 64, h, rr * N + jt * kTileN,
-                      smem_u32(&bars->k_full[st]));
+          for (int kb = 0; kb < C::kKBlocks; ++kb) {
+            if (CL > 1)
+              tma_load_3d_mc(sK + st * C::kKBytes + kb * kTileN * 128, &kv.k[src], kb * 64, h, rr * N + jt * kTileN,
+                             smem_u32(&bars->k_full[st]), kMcMask);
+            else
+              tma_load_3d(sK + st * C::kKBytes + kb * kTileN * 128, &kv.k[src], kb * 64, h, rr * N + jt * kTileN,
+                          smem_u32(&bars->k_full[st]));
+          }
+        }
       }
       __syncwarp();
     };
-    auto load_v = [&](int lv) {
+    auto load_v = [&](int lv, bool refill) {
       const int p = lv / C::kTiles, jt = lv % C::kTiles;
-      const int rr = partner[p * R + r];
+      const int pr = partner[p * R + r];
+      const int src = pr / rows_per_src, rr = pr - src * rows_per_src;
       const int st = lv % C::kVStages;
+      const bool mine = (CL == 1) || ((uint32_t)(lv % CL) == crank);
+      if (refill && mine) mbar_wait(smem_u32(&bars->v_empty[st]), ((lv / C::kVStages) - 1) & 1);
       if (elect_one()) {
         mbar_expect_tx(smem_u32(&bars->v_full[st]), C::kVBytes);
-        tma_load_2d(sV + st * C::kVBytes, &tmV, jt * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
+        if (mine) {
+          if (CL > 1)
+            tma_load_2d_mc(sV + st * C::kVBytes, &kv.v[src], jt * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]),
+                           kMcMask);
+          else
+            tma_load_2d(sV + st * C::kVBytes, &kv.v[src], jt * kTileN, (rr * H + h) * C::kDV, smem_u32(&bars->v_full[st]));
+        }
       }
       __syncwarp();
     };
@@ -235,7 +280,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                   kIdescQK, ks > 0);
         }
         umma_commit(smem_u32(&bars->s_full));
-        umma_commit(smem_u32(&bars->k_empty[st]));
+        if (CL > 1) umma_commit_mc(smem_u32(&bars->k_empty[st]), kMcMask);
+        else umma_commit(smem_u32(&bars->k_empty[st]));
       }
       __syncwarp();
     };
@@ -246,8 +292,8 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_load_3d(sQ + kb * kBlockM * 128, &tmQ, kb * 64, h, r * N + qt * kBlockM, smem_u32(&bars->q_full));
     }
     __syncwarp();
-    for (int lt = 0; lt < C::kKStages && lt < total; ++lt) load_k(lt);
-    for (int lv = 0; lv < C::kVStages && lv < total; ++lv) load_v(lv);
+    for (int lt = 0; lt < C::kKStages && lt < total; ++lt) load_k(lt, false);
+    for (int lv = 0; lv < C::kVStages && lv < total; ++lv) load_v(lv, false);
     mbar_wait(smem_u32(&bars->q_full), 0);
     issue_qk(0);
     for (int j = 0; j < total; ++j) {
@@ -257,20 +303,14 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (DBG && j < 32 && lane == 0)
         ms = reinterpret_cast<long long*>(dbg + (size_t)gridDim.x * kBlockM * kTileN) + ((size_t)(gridDim.x + blockIdx.x) * 32 + j) * 8;
       if (DBG && ms) ms[0] = clock64();
-      if (j + C::kKStages < total) {       // Q K_j^T has read its K stage: refill it
-        mbar_wait(smem_u32(&bars->k_empty[j % C::kKStages]), (j / C::kKStages) & 1);
-        load_k(j + C::kKStages);
-      }
+      if (j + C::kKStages < total) load_k(j + C::kKStages, true);   // Q K_j^T has read its K stage: refill it
       if (!C::kAliasP && j + 1 < total) {
         mbar_wait(smem_u32(&bars->s_free), j & 1);
         if (DBG && ms) ms[1] = clock64();
         issue_qk(j + 1);
       }
       if (DBG && ms) ms[2] = clock64();
-      if (j >= 1 && j - 1 + C::kVStages < total) {   // P V_{j-1} has read its V stage: refill it
-        mbar_wait(smem_u32(&bars->v_empty[(j - 1) % C::kVStages]), ((j - 1) / C::kVStages) & 1);
-        load_v(j - 1 + C::kVStages);
-      }
+      if (j >= 1 && j - 1 + C::kVStages < total) load_v(j - 1 + C::kVStages, true);   // P V_{j-1} has read its V stage
       mbar_wait(smem_u32(&bars->v_full[st]), (j / C::kVStages) & 1);
       mbar_wait(smem_u32(&bars->p_full), j & 1);
       tc_fence_after();
@@ -282,11 +322,22 @@ epi_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                   (j > 0) || (ks > 0));
         umma_commit(smem_u32(&bars->pv_done));
         if (j == total - 1) umma_commit(smem_u32(&bars->o_done));
-        umma_commit(smem_u32(&bars->v_empty[st]));
+        if (CL > 1) umma_commit_mc(smem_u32(&bars->v_empty[st]), kMcMask);
+        else umma_commit(smem_u32(&bars->v_empty[st]));
       }
       __syncwarp();
       if (C::kAliasP && j + 1 < total) issue_qk(j + 1);
       if (DBG && ms) ms[4] = clock64();
+    }
+    if (CL > 1) {
+      // A CTA may only leave once no peer can still signal it: the last use of every stage must have collected the
+      // commit arrivals of ALL CTAs of the cluster (their final MMAs on that stage have completed).
+#pragma unroll
+      for (int st = 0; st < C::kKStages; ++st)
+        if (st < total) mbar_wait(smem_u32(&bars->k_empty[st]), (((total - 1 - st) / C::kKStages)) & 1);
+#pragma unroll
+      for (int st = 0; st < C::kVStages; ++st)
+        if (st < total) mbar_wait(smem_u32(&bars->v_empty[st]), (((total - 1 - st) / C::kVStages)) & 1);
     }
   } else {
     // =============================== softmax warps ==============================
@@ -671,17 +722,26 @@ static int make_map_heads(CUtensorMap* m, const void* base, uint64_t rows, uint6
   });
 }
 
-template <int D, int FEAT>
-static int launch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                  int R_kv, int H, int n_partners, float S, float* dbg, float* lse, cudaStream_t st) {
-  using C = Cfg<D, FEAT>;
+template <int D, int FEAT, int CL>
+static int launch(const void* q, const KvSrc& src, const float* rowp, const int* partner, void* out, int R, int H,
+                  int n_partners, float S, float* dbg, float* lse, cudaStream_t st) {
+  using C = Cfg<D, FEAT, CL>;
   constexpr int N = FEAT * FEAT;
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ;
+  KvMaps kv;
   int rc;
   if ((rc = make_map_heads(&tmQ, q, (uint64_t)R * N, (uint64_t)H, (uint64_t)D, kBlockM)) != CVD_OK) return rc;
-  if ((rc = make_map_heads(&tmK, k, (uint64_t)R_kv * N, (uint64_t)H, (uint64_t)D, kTileN)) != CVD_OK) return rc;
-  if ((rc = make_map(&tmV, vt, (uint64_t)R_kv * H * C::kDV, (uint64_t)N, C::kDV)) != CVD_OK) return rc;
-  constexpr bool kHasDebug = (D == 40 && FEAT == 32);   // the S-dump variant is built for the bench shape only
+  for (int i = 0; i < kMaxSrc; ++i) {
+    const int j = i < src.n_src ? i : 0;          // unused slots repeat source 0 (never addressed)
+    if (i < src.n_src) {
+      if ((rc = make_map_heads(&kv.k[i], src.k[j], (uint64_t)src.rows_per_src * N, (uint64_t)H, (uint64_t)D, kTileN)) != CVD_OK) return rc;
+      if ((rc = make_map(&kv.v[i], src.v[j], (uint64_t)src.rows_per_src * H * C::kDV, (uint64_t)N, C::kDV)) != CVD_OK) return rc;
+    } else {
+      kv.k[i] = kv.k[0];
+      kv.v[i] = kv.v[0];
+    }
+  }
+  constexpr bool kHasDebug = (D == 40 && FEAT == 32 && CL == 1);   // the S-dump variant is built for the bench shape only
   CVD_REQUIRE(dbg == nullptr || kHasDebug, "cvd_epi_attn_fwd_debug: only (head_dim=40, feat=32) has a debug build");
   // CVD_ATTN_PIPE=0 selects the un-pipelined softmax loop at the bench shape (A/B measurements only)
   static int pipe = -1;
@@ -689,47 +749,74 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
     const char* e = getenv("CVD_ATTN_PIPE");
     pipe = (e != nullptr && e[0] == '0' && kHasDebug) ? 0 : 1;
   }
-  auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug, true>
-                                            : (pipe ? epi_attn_fwd_kernel<D, FEAT, false, true>
-                                                    : epi_attn_fwd_kernel<D, FEAT, false, !kHasDebug>);
+  auto kern = (dbg != nullptr && kHasDebug) ? epi_attn_fwd_kernel<D, FEAT, kHasDebug, true, CL>
+                                            : (pipe ? epi_attn_fwd_kernel<D, FEAT, false, true, CL>
+                                                    : epi_attn_fwd_kernel<D, FEAT, false, !kHasDebug, CL>);
   CVD_CUDA(ensure_dynamic_smem((const void*)kern, C::kSmemBytes));
   constexpr int kQTiles = (N + kBlockM - 1) / kBlockM;
+  static_assert(kQTiles % CL == 0, "a cluster holds query tiles of ONE (row, head)");
   const long long grid = (long long)R * H * kQTiles;
   CVD_REQUIRE(grid > 0 && grid < (1ll << 31), "cvd_epi_attn_fwd: grid of %lld CTAs", grid);
-  CVD_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)C::kSmemBytes, st, tmQ, tmK, tmV, rowp, partner,
-                      (__nv_bfloat16*)out, R, H, n_partners, S / (float)FEAT, dbg, lse));
+  CVD_CUDA(launch_pdl_cluster(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)C::kSmemBytes, st, (unsigned)CL, tmQ, kv, rowp,
+                              partner, (__nv_bfloat16*)out, R, H, n_partners, src.rows_per_src, S / (float)FEAT, dbg, lse));
   CVD_LAUNCH_CHECK("epi_attn_fwd_kernel");
   return CVD_OK;
 }
 
+// CVD_ATTN_CLUSTER=1: use the cluster-multicast kernels for LOCAL K / V^T too (A/B measurements); sharded calls
+// (cvd_epi_attn_fwd_sharded) always use them where a (row, head) has more than one query tile.
+static bool cluster_local() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVD_ATTN_CLUSTER");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
-
-static int dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, int R,
-                    int R_kv, int N, int heads, int head_dim, int n_partners, int feat, float S, float* dbg, float* lse,
-                    cudaStream_t st) {
-  CVD_REQUIRE(q && k && vt && partner && out, "cvd_epi_attn_fwd: null pointer");
-  CVD_REQUIRE(R > 0 && R_kv > 0 && heads > 0 && n_partners >= 1, "cvd_epi_attn_fwd: R=%d R_kv=%d heads=%d n_partners=%d", R, R_kv, heads,
-              n_partners);
+static int dispatch(const void* q, const KvSrc& src, const float* rowp, const int* partner, void* out, int R, int N, int heads,
+                    int head_dim, int n_partners, int feat, float S, float* dbg, float* lse, bool multicast, cudaStream_t st) {
+  CVD_REQUIRE(q && partner && out, "cvd_epi_attn_fwd: null pointer");
+  CVD_REQUIRE(src.n_src >= 1 && src.n_src <= kMaxSrc && src.rows_per_src > 0, "cvd_epi_attn_fwd: %d K/V sources of %d rows", src.n_src,
+              src.rows_per_src);
+  CVD_REQUIRE(R > 0 && heads > 0 && n_partners >= 1, "cvd_epi_attn_fwd: R=%d heads=%d n_partners=%d", R, heads, n_partners);
   CVD_REQUIRE(N == feat * feat, "cvd_epi_attn_fwd: N=%d is not feat^2 (feat=%d); only square latents are supported", N, feat);
-  CVD_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out) & 15) == 0,
-              "cvd_epi_attn_fwd: q/k/vt/out must be 16-byte aligned");
+  uintptr_t bits = (uintptr_t)q | (uintptr_t)out;
+  for (int i = 0; i < src.n_src; ++i) {
+    CVD_REQUIRE(src.k[i] && src.v[i], "cvd_epi_attn_fwd: null K / V^T pointer (source %d)", i);
+    bits |= (uintptr_t)src.k[i] | (uintptr_t)src.v[i];
+  }
+  CVD_REQUIRE((bits & 15) == 0, "cvd_epi_attn_fwd: q/k/vt/out must be 16-byte aligned");
   if (dbg == nullptr && feat <= 4) {   // 4x4 latent grid: warp-level kernel (a 128x64 tcgen05 tile would be 97 % padding; 6.5 vs 11 us)
-    const int rc = epi_attn_small_dispatch(q, k, vt, rowp, partner, out, lse, R, heads, head_dim, n_partners, feat, S, st);
+    const int rc = epi_attn_small_dispatch(q, src, rowp, partner, out, lse, R, heads, head_dim, n_partners, feat, S, st);
     if (rc != -1000) return rc;
   }
-#define CVD_CASE(D_, F_) \
-  if (head_dim == D_ && feat == F_) return launch<D_, F_>(q, k, vt, rowp, partner, out, R, R_kv, heads, n_partners, S, dbg, lse, st);
-  CVD_CASE(40, 32)
-  CVD_CASE(40, 64)
-  CVD_CASE(80, 16)
-  CVD_CASE(80, 32)
-  CVD_CASE(160, 16)
-  CVD_CASE(40, 16)
-  CVD_CASE(160, 8)
-  CVD_CASE(80, 8)
-  CVD_CASE(40, 8)
+  const bool mc = dbg == nullptr && (multicast || cluster_local());
+#define CVD_CASE(D_, F_, CL_)                                                                                       \
+  if (head_dim == D_ && feat == F_) {                                                                               \
+    if (mc && CL_ > 1) return launch<D_, F_, CL_>(q, src, rowp, partner, out, R, heads, n_partners, S, dbg, lse, st); \
+    return launch<D_, F_, 1>(q, src, rowp, partner, out, R, heads, n_partners, S, dbg, lse, st);                     \
+  }
+  CVD_CASE(40, 32, 8)
+  CVD_CASE(40, 64, 8)
+  CVD_CASE(80, 16, 2)
+  CVD_CASE(80, 32, 8)
+  CVD_CASE(160, 16, 2)
+  CVD_CASE(40, 16, 2)
+  CVD_CASE(160, 8, 1)
+  CVD_CASE(80, 8, 1)
+  CVD_CASE(40, 8, 1)
 #undef CVD_CASE
   return fail(CVD_E_INVALID, "cvd_epi_attn_fwd: (head_dim=%d, feat=%d) is not an instantiated configuration", head_dim, feat);
+}
+
+static KvSrc one_source(const void* k, const void* vt, int R_kv) {
+  KvSrc s = {};
+  s.k[0] = k;
+  s.v[0] = vt;
+  s.n_src = 1;
+  s.rows_per_src = R_kv;
+  return s;
 }
 
 }  // namespace sm100
@@ -738,18 +825,40 @@ static int dispatch(const void* q, const void* k, const void* vt, const float* r
 extern "C" int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, const float* rowp, const int* partner,
                                 void* out, int R, int R_kv, int N, int heads, int head_dim, int n_partners, int feat,
                                 float F_mat_size, cvd_stream_t stream) {
-  return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr,
-                              nullptr, (cudaStream_t)stream);
+  CVD_REQUIRE(R_kv > 0, "cvd_epi_attn_fwd: R_kv=%d", R_kv);
+  return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
+                              F_mat_size, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 
-// Same, additionally writing the base-2 log-sum-exp of every (row, head, query) -- the statistic the backward pass
-// (cvd_epi_attn_bwd) recomputes the probabilities from.  lse: fp32 [R, heads, N].
+// View-sharded form: K / V^T of the partner rows live in n_src buffers of rows_per_src rows each (the symmetric-memory
+// buffers of the GPUs of one NVSwitch box, passed as peer-mapped device pointers, own rank included); `partner` holds
+// GLOBAL rows.  The kernel reads the partner tiles straight out of the owning GPU's HBM; where a (row, head) has several
+// query tiles they form a thread-block cluster and every tile crosses NVLink once (TMA multicast).
+extern "C" int cvd_epi_attn_fwd_sharded(const void* q, const void* const* k_srcs, const void* const* vt_srcs, int n_src,
+                                        int rows_per_src, const float* rowp, const int* partner, void* out, int R, int N,
+                                        int heads, int head_dim, int n_partners, int feat, float F_mat_size,
+                                        cvd_stream_t stream) {
+  CVD_REQUIRE(k_srcs && vt_srcs && n_src >= 1 && n_src <= cvd::kMaxKvSrc, "cvd_epi_attn_fwd_sharded: n_src=%d (1..%d)", n_src,
+              cvd::kMaxKvSrc);
+  cvd::KvSrc s = {};
+  for (int i = 0; i < n_src; ++i) {
+    s.k[i] = k_srcs[i];
+    s.v[i] = vt_srcs[i];
+  }
+  s.n_src = n_src;
+  s.rows_per_src = rows_per_src;
+  return cvd::sm100::dispatch(q, s, rowp, partner, out, R, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr, nullptr,
+                              true, (cudaStream_t)stream);
+}
+
+// Same as cvd_epi_attn_fwd, additionally writing the base-2 log-sum-exp of every (row, head, query) -- the statistic the
+// backward pass (cvd_epi_attn_bwd) recomputes the probabilities from.  lse: fp32 [R, heads, N].
 extern "C" int cvd_epi_attn_fwd_lse(const void* q, const void* k, const void* vt, const float* rowp, const int* partner,
                                     void* out, float* lse, int R, int R_kv, int N, int heads, int head_dim, int n_partners,
                                     int feat, float F_mat_size, cvd_stream_t stream) {
-  CVD_REQUIRE(lse != nullptr, "cvd_epi_attn_fwd_lse: null lse");
-  return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr,
-                              lse, (cudaStream_t)stream);
+  CVD_REQUIRE(lse != nullptr && R_kv > 0, "cvd_epi_attn_fwd_lse: null lse / R_kv=%d", R_kv);
+  return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
+                              F_mat_size, nullptr, lse, false, (cudaStream_t)stream);
 }
 
 // Bring-up aid: additionally dumps the raw Q K^T accumulator of key tile 0 of every CTA
@@ -757,6 +866,7 @@ extern "C" int cvd_epi_attn_fwd_lse(const void* q, const void* k, const void* vt
 extern "C" int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* vt, const float* rowp, const int* partner,
                                       void* out, float* dbg_s, int R, int R_kv, int N, int heads, int head_dim,
                                       int n_partners, int feat, float F_mat_size, cvd_stream_t stream) {
-  return cvd::sm100::dispatch(q, k, vt, rowp, partner, out, R, R_kv, N, heads, head_dim, n_partners, feat, F_mat_size, dbg_s,
-                              nullptr, (cudaStream_t)stream);
+  CVD_REQUIRE(R_kv > 0, "cvd_epi_attn_fwd_debug: R_kv=%d", R_kv);
+  return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
+                              F_mat_size, dbg_s, nullptr, false, (cudaStream_t)stream);
 }

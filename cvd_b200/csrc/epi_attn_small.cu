@@ -38,9 +38,9 @@ __device__ __forceinline__ uint32_t ldg_u32(const __nv_bfloat16* p) { return __l
 // One warp task = 16 query rows [m0, m0+16) of (row r, head h).
 template <int D, int FEAT, int KP>   // KP: partners whose keys are concatenated (1 or 2)
 __global__ void __launch_bounds__(kWarps * 32)
-epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                      const __nv_bfloat16* __restrict__ vt, const float* __restrict__ rowp, const int* __restrict__ partner,
-                      __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int R, int H, float step) {
+epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const KvSrc kv, const float* __restrict__ rowp,
+                      const int* __restrict__ partner, __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int R, int H,
+                      float step) {
   constexpr int N = FEAT * FEAT;
   constexpr int kMBlocks = N / 16;                 // 16-row query blocks per (row, head)
   constexpr int kKSteps = (D + 15) / 16;           // k steps of Q K^T
@@ -80,8 +80,9 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int p = 0; p < KP; ++p) {
-    const int rr = partner[p * R + r];
-    const __nv_bfloat16* kb = k + (size_t)rr * N * C + h * D;
+    const int pr = partner[p * R + r];
+    const int src = pr / kv.rows_per_src, rr = pr - src * kv.rows_per_src;
+    const __nv_bfloat16* kb = (const __nv_bfloat16*)kv.k[src] + (size_t)rr * N * C + h * D;
 #pragma unroll
     for (int nt = 0; nt < kNT; ++nt) {
       s[p][nt][0] = s[p][nt][1] = s[p][nt][2] = s[p][nt][3] = 0.f;
@@ -166,8 +167,9 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
-      const int rr = partner[p * R + r];
-      const __nv_bfloat16* vrow = vt + ((size_t)(rr * H + h) * kDV + dt * 8 + g) * N;   // B operand: dim = dt*8 + g, keys (t*2, +1) (+8)
+      const int pr = partner[p * R + r];
+      const int src = pr / kv.rows_per_src, rr = pr - src * kv.rows_per_src;
+      const __nv_bfloat16* vrow = (const __nv_bfloat16*)kv.v[src] + ((size_t)(rr * H + h) * kDV + dt * 8 + g) * N;   // B operand: dim = dt*8 + g, keys (t*2, +1) (+8)
 #pragma unroll
       for (int kk = 0; kk < N / 16; ++kk) {
         const uint32_t a[4] = {pa[p][2 * kk][0], pa[p][2 * kk][1], pa[p][2 * kk + 1][0], pa[p][2 * kk + 1][1]};
@@ -181,8 +183,8 @@ epi_attn_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
 }
 
 template <int D, int FEAT>
-static int launch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out, float* lse,
-                  int R, int H, int n_partners, float S, cudaStream_t st) {
+static int launch(const void* q, const KvSrc& kv, const float* rowp, const int* partner, void* out, float* lse, int R, int H,
+                  int n_partners, float S, cudaStream_t st) {
   constexpr int N = FEAT * FEAT;
   const long long tasks = (long long)R * H * (N / 16);
   const long long grid = (tasks + kWarps - 1) / kWarps;
@@ -191,10 +193,10 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
   const float step = S / (float)FEAT;
   if (n_partners == 1)
     CVD_CUDA(launch_pdl(epi_attn_small_kernel<D, FEAT, 1>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, (const __nv_bfloat16*)q,
-                        (const __nv_bfloat16*)k, (const __nv_bfloat16*)vt, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
+                        kv, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
   else
     CVD_CUDA(launch_pdl(epi_attn_small_kernel<D, FEAT, 2>, dim3((unsigned)grid), dim3(kWarps * 32), 0, st, (const __nv_bfloat16*)q,
-                        (const __nv_bfloat16*)k, (const __nv_bfloat16*)vt, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
+                        kv, rowp, partner, (__nv_bfloat16*)out, lse, R, H, step));
   CVD_LAUNCH_CHECK("epi_attn_small_kernel");
   return CVD_OK;
 }
@@ -203,10 +205,10 @@ static int launch(const void* q, const void* k, const void* vt, const float* row
 
 // Returns CVD_OK / an error if (head_dim, feat) is a small-grid configuration, and -1000 if it is not
 // (the caller then uses the tcgen05 kernel).
-int epi_attn_small_dispatch(const void* q, const void* k, const void* vt, const float* rowp, const int* partner, void* out,
-                            float* lse, int R, int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st) {
+int epi_attn_small_dispatch(const void* q, const KvSrc& kv, const float* rowp, const int* partner, void* out, float* lse, int R,
+                            int heads, int head_dim, int n_partners, int feat, float S, cudaStream_t st) {
 #define CVD_CASE(D_, F_) \
-  if (head_dim == D_ && feat == F_) return small::launch<D_, F_>(q, k, vt, rowp, partner, out, lse, R, heads, n_partners, S, st);
+  if (head_dim == D_ && feat == F_) return small::launch<D_, F_>(q, kv, rowp, partner, out, lse, R, heads, n_partners, S, st);
   CVD_CASE(160, 4)
   CVD_CASE(80, 4)
   CVD_CASE(40, 4)

@@ -103,6 +103,32 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// ---- thread-block clusters: rank, cluster barrier, multicast TMA, multicast commit ----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster (release / acquire: makes mbarrier inits visible cluster-wide)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One global read, delivered to the SAME shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at
+// the same offset as `bar` receives the complete_tx of its copy.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* m, int x, int y, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"((uint64_t)m), "r"(x), "r"(y), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* m, int x, int y, int z, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+      "l"((uint64_t)m), "r"(x), "r"(y), "r"(z), "r"(bar), "h"(mask)
+      : "memory");
+}
+
 // ---- TMEM allocation (one full warp) ----------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
@@ -164,6 +190,13 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 // Make the mbarrier track completion of all tcgen05 ops issued so far by this thread.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Same, arriving on the mbarrier at this offset in EVERY CTA of `mask` (cluster-wide "this CTA is done with the stage").
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // ---- TMEM <-> registers (32 lanes x 32 bit, N consecutive columns per thread) -----------

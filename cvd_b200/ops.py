@@ -88,6 +88,38 @@ def epi_attn_fwd(q, k, vt, rowp, partner, heads, F_mat_size, dbg_s=None):
     return out
 
 
+def epi_attn_fwd_sharded(q, k_srcs, vt_srcs, rows_per_src, rowp, partner, heads, F_mat_size):
+    """View-sharded attention with the exchange fused into the kernel (``cvd_epi_attn_fwd_sharded``).
+
+    ``k_srcs`` / ``vt_srcs``: one tensor per source rank (``[rows_per_src, N, C]`` / ``[rows_per_src, H, DV, N]`` bf16:
+    the symmetric-memory buffers of every rank seen through their peer mappings, own rank included) or plain device
+    pointers; ``partner`` int32 holds GLOBAL rows (source = row // rows_per_src).  The caller has ordered the call
+    after the peers' writes (symmetric-memory barrier)."""
+    import ctypes
+    R, N, C = q.shape
+    d = C // heads
+    n_src = len(k_srcs)
+    assert 1 <= n_src <= 8 and len(vt_srcs) == n_src
+    n_partners = partner.shape[0] // R
+    assert partner.shape[0] == n_partners * R
+    feat = int(round(N ** 0.5))
+
+    def ptr(t, shape):
+        if isinstance(t, torch.Tensor):
+            assert tuple(t.shape) == shape, (tuple(t.shape), shape)
+            return _check(t, torch.bfloat16, "k / vt source")
+        return int(t)
+    ka = (ctypes.c_void_p * n_src)(*[ptr(t, (rows_per_src, N, C)) for t in k_srcs])
+    va = (ctypes.c_void_p * n_src)(*[ptr(t, (rows_per_src, heads, dv_rows(d), N)) for t in vt_srcs])
+    out = torch.empty_like(q)
+    _lib.call("cvd_epi_attn_fwd_sharded", _check(q, torch.bfloat16, "q"), ctypes.cast(ka, ctypes.c_void_p),
+              ctypes.cast(va, ctypes.c_void_p), n_src, rows_per_src, None if rowp is None else _check(rowp, torch.float32, "rowp"),
+              _check(partner, torch.int32, "partner"), out.data_ptr(), R, N, heads, d, n_partners, feat, float(F_mat_size),
+              _stream())
+    _count()
+    return out
+
+
 def epi_attn_fwd_lse(q, k, vt, rowp, partner, heads, F_mat_size):
     """:func:`epi_attn_fwd` that also returns lse fp32 [R,H,N] (base-2 log-sum-exp of every query row's logits)."""
     R, R_kv, N, d, n_partners, feat = _attn_args(q, k, vt, rowp, partner, heads)

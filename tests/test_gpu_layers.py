@@ -200,14 +200,46 @@ def test_temporal_module_vs_reference_fixture(golden, dev, case):
     assert_close(y.cpu() - x.cpu(), ref - x.cpu(), rel=3e-2, what=name + " (module delta)")
 
 
-def test_training_mode_is_refused_by_the_temporal_module(dev):
-    """The motion module is frozen in train_epi_control.py (only the epi parameters train, :270-283) and its kernels are
-    forward-only: asked for a graph, it refuses instead of silently detaching.  (The epi module trains:
-    tests/test_gpu_training.py.)"""
+def test_temporal_module_train_twin_vs_oracle_autograd(golden, dev):
+    """The motion module is frozen in train_epi_control.py (only the epi parameters train, :270-283) but the gradients of
+    the epi modules in front of it flow THROUGH it (:589-630), so in train() mode it records an autograd graph
+    (``forward_train``) instead of refusing.  Forward, d/dx and d/dpose against torch autograd through the fp32 CPU
+    oracle (pinned to the reference's temporal fixtures) on the fixture's own state dict: module delta rel-L2 3e-2,
+    gradients 5e-2 (bf16 GEMM operands vs fp32), and the twin equals the CUDA inference path to bf16 rounding."""
     import cvd_b200
-    m = cvd_b200.VanillaTemporalModule(320, num_attention_heads=8, num_transformer_block=1,
-                                       attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
-                                       temporal_position_encoding_max_len=32, zero_initialize=False).to(dev).train()
-    x = torch.zeros(2, 320, 16, 4, 4, device=dev)
-    with pytest.raises(NotImplementedError):
-        m(x, cross_attention_kwargs={"pose_feature": None})
+    from gpu_util import rel_l2
+    from oracle import epi_oracle as O
+    case = gi.TEMPORAL_CASES[0]
+    assert case["pose"]
+    C, feat, B = case["C"], case["feat"], case["B"]
+    sd = gi.temporal_state_dict(C, case["seed"])
+    m = cvd_b200.VanillaTemporalModule(C, num_attention_heads=8, num_transformer_block=1,
+                                       attention_block_types=["Temporal_Self", "Temporal_Self"],
+                                       temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                                       zero_initialize=False)
+    blk = m.temporal_transformer.transformer_blocks[0]
+    blk.attention_blocks[0].set_processor(cvd_b200.PoseAdaptorAttnProcessor(
+        hidden_size=C, pose_feature_dim=C, query_condition=True, key_value_condition=True, scale=1.0))
+    blk.attention_blocks[1].set_processor(cvd_b200.AttnProcessor(attn_type="temporal"))
+    m.load_state_dict(sd, strict=False)
+    m = m.to(dev)
+    x = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 1)
+    pose = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 2)
+    wgt = gi.hidden_video(B, C, 16, feat, feat, case["seed"] + 3)
+    # oracle, fp32 CPU autograd
+    x_ref, p_ref = x.clone().requires_grad_(True), pose.clone().requires_grad_(True)
+    mk = "temporal_transformer.transformer_blocks.0.attention_blocks.0.processor.qkv_merge."
+    y_ref = O.temporal_module(x_ref, sd, 8, p_ref, merges=[(sd[mk + "weight"], sd[mk + "bias"]), None])
+    (y_ref * wgt).sum().backward()
+    # product
+    with torch.no_grad():
+        y_inf = m.eval()(x.to(dev), cross_attention_kwargs={"pose_feature": pose.to(dev)})
+    xp, pp = x.to(dev).requires_grad_(True), pose.to(dev).requires_grad_(True)
+    y = m.train()(xp, cross_attention_kwargs={"pose_feature": pp})
+    assert y.shape == x.shape and y.dtype == x.dtype
+    (y * wgt.to(dev)).sum().backward()
+    e_same = rel_l2(y.detach().cpu() - x, y_inf.cpu() - x)
+    e_fwd = rel_l2(y.detach().cpu() - x, y_ref.detach() - x)
+    e_x, e_p = rel_l2(xp.grad.cpu(), x_ref.grad), rel_l2(pp.grad.cpu(), p_ref.grad)
+    print(f"temporal train twin: vs inference path {e_same:.2e}, vs oracle {e_fwd:.2e}, d/dx {e_x:.2e}, d/dpose {e_p:.2e}")
+    assert e_same < 1e-2 and e_fwd < 3e-2 and e_x < 5e-2 and e_p < 5e-2
