@@ -18,10 +18,12 @@ sum 4*R*N*N*C = 15.32 GFLOP * R (softmax, bias and MMA padding excluded).
   --impl reference : the reference's CPU path (oracle port of EpiSelfAttention.forward, fp32,
           all host threads) on a bounded sample of the same step (one call per shape).
 At N > 1 the views shard across ranks (weak scaling: 64 rows per GPU, 2N views); K and V^T live in
-symmetric memory and every call moves exactly its partner rows across NVLink after one device-side
-barrier -- by the copy engines in two row chunks, the attention of chunk 0 running under the
-transfer of chunk 1 (--exchange dma, default), by our pull kernel (--exchange peer), or as an NCCL
-all-gather of every rank's rows (--exchange allgather, the baseline).
+symmetric memory and every call reads exactly its partner rows across NVLink after one device-side
+barrier.  --exchange fused (default): the exchange is INSIDE the attention kernel
+(cvd_epi_attn_fwd_sharded): TMA reads of the peer's tiles, multicast to the query-tile CTAs of a
+(row, head) cluster, so every byte crosses NVLink once, under the softmax.  Baselines: dma (copy
+engines, two row chunks, attention of chunk 0 under the transfer of chunk 1), peer (our pull
+kernel), allgather (NCCL all-gather of every rank's rows).
 """
 import argparse
 import json
@@ -44,7 +46,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
-EXCHANGE = "NVLink copy engines, 2 row chunks under the attention; grids <= 8x8 read the peer's K/V^T in-kernel (TMA over NVLink)"
+EXCHANGE = "fused into the attention kernel: TMA reads of the peer's K/V^T tiles over NVLink, cluster multicast to the query-tile CTAs of a (row, head)"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -302,7 +304,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
-        if args.exchange in ("peer", "dma"):
+        if args.exchange in ("peer", "dma", "fused"):
             peer = sharding.PeerExchange(shard)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _lib.load()
@@ -387,6 +389,19 @@ def run_ours(args):
                     ks, vs = k, vt
                 elif peer is None:            # baseline: NCCL all-gather of every rank's K and V^T
                     ks, vs = shard.gather_rows(k), shard.gather_rows(vt)
+                elif args.exchange == "fused":
+                    # one cross-rank barrier (the partner's K / V^T of this call are complete), then ONE kernel: the
+                    # attention reads the partner tiles out of the peer's HBM itself (global partner rows)
+                    xk[1].barrier()
+                    if record and feat == SHAPES[0][0]:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        ops.epi_attn_fwd_sharded(q, xk[2], xv[2], R, rowp, partner, HEADS, F_MAT_SIZE)
+                        e1.record()
+                        big_events.append((e0, e1, 1))
+                    else:
+                        ops.epi_attn_fwd_sharded(q, xk[2], xv[2], R, rowp, partner, HEADS, F_MAT_SIZE)
+                    continue
                 elif args.exchange == "dma":
                     # one cross-rank barrier, then the partner rows cross NVLink on the COPY ENGINES in two row chunks on a
                     # side stream; the attention of chunk 0 runs under the transfer of chunk 1 (no SMs are spent on the pull)
@@ -570,15 +585,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
-    ap.add_argument("--exchange", default="dma", choices=["peer", "dma", "allgather"],
-                    help="N>1: pull partner rows over NVLink peer memory with our kernel (peer), with the copy engines in two "
-                         "row chunks overlapped with the attention (dma), or NCCL all-gather (baseline)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "dma", "allgather"],
+                    help="N>1: read the partner rows inside the attention kernel (fused: TMA over NVLink, cluster multicast), "
+                         "pull them with our kernel (peer), with the copy engines in two row chunks overlapped with the "
+                         "attention (dma), or NCCL all-gather (baseline)")
     args = ap.parse_args()
     global EXCHANGE
     if args.exchange == "allgather":
         EXCHANGE = "NCCL all-gather"
     if args.exchange == "peer":
         EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
+    if args.exchange == "dma":
+        EXCHANGE = "NVLink copy engines, 2 row chunks under the attention; grids <= 8x8 read the peer's K/V^T in-kernel (TMA over NVLink)"
     if args.impl == "reference":
         run_reference(args)
     else:

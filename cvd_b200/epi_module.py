@@ -153,7 +153,8 @@ class _Aux(dict):
     def __getitem__(self, name):
         if name == "key" and super().__getitem__("key") is None:
             R, N, C = self["query"].shape
-            kk = self._k[self._partner.long()]
+            k_all = torch.cat(list(self._k), dim=0) if isinstance(self._k, (list, tuple)) else self._k
+            kk = k_all[self._partner.long()]
             if kk.shape[0] != R:
                 kk = kk.reshape(-1, R, N, C).permute(1, 2, 0, 3).reshape(R, -1, C)
             self["key"] = kk
@@ -227,6 +228,22 @@ class EpiAttnProcessor(nn.Module):
             partner = self.partner_index(R, kv_index, x.device)
         w = attn._w
         q = F.linear(x, w.bf16("q", attn.to_q.weight))
+        if self.peer is not None and getattr(self.peer, "mode", "hidden") == "fused":
+            # view sharding, product path: K / V^T of the LOCAL rows go straight into symmetric memory (the GEMMs write
+            # them there); one cross-rank barrier; the attention kernel reads the partner rows' tiles out of the peers'
+            # HBM itself -- the exchange runs inside the kernel, under the softmax (cvd_epi_attn_fwd_sharded)
+            DV = ops.dv_rows(d)
+            k_loc, k_all, hk = self.peer.slot_views((R, N, C), torch.bfloat16, x.device)
+            vt_loc, vt_all, _hv = self.peer.slot_views((R, H, DV, N), torch.bfloat16, x.device)
+            torch.mm(x.view(R * N, C), w.bf16("k", attn.to_k.weight).t(), out=k_loc.view(R * N, C))   # == F.linear
+            torch.matmul(attn.padded_v_weights(), x.transpose(1, 2), out=vt_loc.view(R, H * DV, N))
+            vt_loc[:, :, d].fill_(1.0)
+            hk.barrier()
+            o = ops.epi_attn_fwd_sharded(q, k_all, vt_all, R, epi_rowp, partner, H, attn.F_mat_size)
+            if fix_firstframe:
+                o = self._fix_firstframe(attn, x, o, ff_group)
+            y = F.linear(o, w.bf16("o", attn.to_out[0].weight))
+            return y, _Aux(q, k_all, partner)
         x_kv = x
         if self.peer is not None:
             # view sharding, product path: pull the partner rows of the (LayerNorm-ed) hidden states out of the
@@ -245,15 +262,21 @@ class EpiAttnProcessor(nn.Module):
             k_src, vt_src = self.shard.gather_rows(k), self.shard.gather_rows(vt)
         o = ops.epi_attn_fwd(q, k_src, vt_src, epi_rowp, partner, H, attn.F_mat_size)
         if fix_firstframe:
-            # attention_processor.py:629-635: first-frame rows take the batch-mean self value; the mean runs over the
-            # rows of ONE processor call, i.e. per chunk of `ff_group` rows in the reference's memory-relief branch
-            # (epi_module.py:436-447)
-            G = R if ff_group is None else ff_group
-            v_self = F.linear(x, w.bf16("v", attn.to_v.weight)).view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)
-            ff = v_self[:, :, :, 0].float().mean(dim=1, keepdim=True).to(o.dtype)
-            o.view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)[:, :, :, 0] = ff
+            o = self._fix_firstframe(attn, x, o, ff_group)
         y = F.linear(o, w.bf16("o", attn.to_out[0].weight))     # bias / rescale are applied by the caller
         return y, _Aux(q, k_src, partner)
+
+    @staticmethod
+    def _fix_firstframe(attn, x, o, ff_group):
+        """attention_processor.py:629-635: first-frame rows take the batch-mean self value; the mean runs over the rows
+        of ONE processor call, i.e. per chunk of ``ff_group`` rows in the reference's memory-relief branch
+        (epi_module.py:436-447)."""
+        R, N, C = x.shape
+        G = R if ff_group is None else ff_group
+        v_self = F.linear(x, attn._w.bf16("v", attn.to_v.weight)).view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)
+        ff = v_self[:, :, :, 0].float().mean(dim=1, keepdim=True).to(o.dtype)
+        o.view(R // G, -1, 2, FRAMES_PER_VIDEO, N, C)[:, :, :, 0] = ff
+        return o
 
 
 class EpiSelfAttention(nn.Module):

@@ -5,13 +5,16 @@ the K/V of a *different view, same frame* (``attention_processor.py:573-583``;
 ``pipeline_animation_epi_advanced.py:621-633``).  So (view, cfg) units shard across ranks with
 one exchange per epi-attention call and no other collective on the path.
 
-Two exchange mechanisms:
+Exchange mechanisms:
 
-* ``PeerExchange`` (product path): the LayerNorm-ed hidden states (layer API) or K / V^T (kernel
-  benchmark) live in symmetric memory; after a device-side cross-rank barrier every rank PULLS
-  exactly the rows its queries attend to out of its peers' HBM with ``cvd_peer_gather_rows``
-  (our kernel, 16-byte loads over NVLink).  R_local rows cross the links per call whatever the
-  world size, and there is no collective launch.
+* ``PeerExchange`` in ``fused`` mode (product path): every rank projects K / V^T of its OWN rows into symmetric
+  memory; after one device-side cross-rank barrier the attention kernel itself reads the partner rows' tiles out of
+  the peers' HBM (``cvd_epi_attn_fwd_sharded``: TMA over NVLink, multicast to the query-tile CTAs of a (row, head)
+  cluster, so every byte crosses the links once and the transfer runs under the softmax).  No landing buffer, no copy
+  launch, no collective.
+* ``PeerExchange`` in ``hidden`` mode: the LayerNorm-ed hidden states live in symmetric memory; after the barrier every
+  rank PULLS exactly the rows its queries attend to with ``cvd_peer_gather_rows`` (our kernel, 16-byte loads over
+  NVLink) and projects K / V^T of those rows locally -- half the bytes, but a separate transfer in front of the GEMMs.
 * ``ViewShard.gather_rows`` (baseline, and the CPU/gloo test path): NCCL all-gather of every rank's
   rows; the attention kernel then indexes the gathered buffer with GLOBAL partner rows.
 
@@ -76,7 +79,12 @@ class PeerExchange:
         self.shard = shard
         self.group = shard.group if shard.group is not None else dist.group.WORLD
         self._slots = {}
+        self._views = {}
         self._arange = {}
+        # "fused": K / V^T of the local rows go to symmetric memory and the attention kernel reads the partner tiles out
+        # of the peers' HBM itself (cvd_epi_attn_fwd_sharded); "hidden": pull the partner rows of the LayerNorm-ed hidden
+        # states with cvd_peer_gather_rows and project them locally (half the bytes, but a separate, exposed transfer)
+        self.mode = "fused"
 
     def alloc(self, shape, dtype, device):
         """One symmetric buffer (a collective call: every rank must allocate in the same order).
@@ -95,6 +103,18 @@ class PeerExchange:
         b = e["bufs"][e["next"]]
         e["next"] ^= 1
         return b
+
+    def slot_views(self, shape, dtype, device):
+        """Next slot of ``shape`` as (local tensor, [every rank's copy of it as a tensor on THIS device, rank order],
+        handle): the K / V^T sources of ``ops.epi_attn_fwd_sharded``."""
+        key = (tuple(shape), dtype)
+        local, ptrs, hdl = self.slot(shape, dtype, device)
+        views = self._views.setdefault(key, {})
+        v = views.get(local.data_ptr())
+        if v is None:
+            v = [hdl.get_buffer(r, tuple(shape), dtype) for r in range(self.shard.world)]
+            views[local.data_ptr()] = v
+        return local, v, hdl
 
     def pull(self, ptrs, hdl, partner, out, rows_per_src):
         """out[r] = peers' row partner[r] (GLOBAL numbering) of an already written symmetric buffer,

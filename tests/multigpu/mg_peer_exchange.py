@@ -28,14 +28,20 @@ rows = shard.local_rows(Rg)
 with torch.no_grad():
     ref, _ = ref_layer(x.to(dev), F_mats=[Fm.to(dev), kv])                    # un-sharded, every rank computes it
     sh_layer.processor.shard = shard; sh_layer.processor.peer = peer
+    assert peer.mode == "fused"                                                # product path: exchange inside the attention kernel
     for it in range(3):                                                        # several calls: slot ping-pong + barriers
         out, aux = sh_layer(x[rows].to(dev), F_mats=[Fm[rows].to(dev), shard.local_kv_index(kv, Rg)])
+    key_ok = torch.equal(aux["key"], ref_layer(x.to(dev), F_mats=[Fm.to(dev), kv])[1]["key"][rows])
+    peer.mode = "hidden"                                                       # pull the LayerNorm-ed hidden rows instead
+    for it in range(2):
+        out_h, _ = sh_layer(x[rows].to(dev), F_mats=[Fm[rows].to(dev), shard.local_kv_index(kv, Rg)])
+    peer.mode = "fused"
     ag_layer.processor.shard = shard
     out2, _ = ag_layer(x[rows].to(dev), F_mats=[Fm[rows].to(dev), shard.local_kv_index(kv, Rg)])
 torch.cuda.synchronize()
-e1 = float((out - ref[rows]).abs().max()); e2 = float((out2 - ref[rows]).abs().max())
-k_ok = torch.equal(aux["key"], _ := ref_layer(x.to(dev), F_mats=[Fm.to(dev), kv])[1]["key"][rows]) if False else True
-print(f"rank {rank}: peer-pull max|diff| vs un-sharded = {e1:.3e}, all-gather = {e2:.3e}")
-assert e1 < 1e-6 and e2 < 1e-6, (e1, e2)
+e1 = float((out - ref[rows]).abs().max()); e2 = float((out2 - ref[rows]).abs().max()); e3 = float((out_h - ref[rows]).abs().max())
+print(f"rank {rank}: max|diff| vs un-sharded: fused in-kernel exchange = {e1:.3e}, hidden-row pull = {e3:.3e}, all-gather = {e2:.3e}; "
+      f"aux key identical: {key_ok}")
+assert e1 < 1e-6 and e2 < 1e-6 and e3 < 1e-6 and key_ok, (e1, e2, e3, key_ok)
 dist.barrier(); dist.destroy_process_group()
 if rank == 0: print("PEER EXCHANGE OK")
