@@ -19,11 +19,10 @@ sum 4*R*N*N*C = 15.32 GFLOP * R (softmax, bias and MMA padding excluded).
           all host threads) on a bounded sample of the same step (one call per shape).
 At N > 1 the views shard across ranks (weak scaling: 64 rows per GPU, 2N views); K and V^T live in
 symmetric memory and every call reads exactly its partner rows across NVLink after one device-side
-barrier.  --exchange fused (default): the exchange is INSIDE the attention kernel
-(cvd_epi_attn_fwd_sharded): TMA reads of the peer's tiles, multicast to the query-tile CTAs of a
-(row, head) cluster, so every byte crosses NVLink once, under the softmax.  Baselines: dma (copy
-engines, two row chunks, attention of chunk 0 under the transfer of chunk 1), peer (our pull
-kernel), allgather (NCCL all-gather of every rank's rows).
+barrier: by the copy engines in row chunks, the smallest first, each chunk's attention running under
+the transfer of the next (--exchange dma, default; latents <= 8x8 are read inside the attention
+kernel by unicast TMA over NVLink), by our pull kernel (--exchange peer), or as an NCCL all-gather of
+every rank's rows (--exchange allgather, the baseline).  The N > 1 step replays as one CUDA graph.
 """
 import argparse
 import json
@@ -46,7 +45,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
-EXCHANGE = "fused into the attention kernel: TMA reads of the peer's K/V^T tiles over NVLink, cluster multicast to the query-tile CTAs of a (row, head)"
+EXCHANGE = "NVLink copy engines in row chunks (smallest first) under the attention, K and V^T on two streams; grids <= 8x8 read the peer's K/V^T in-kernel (unicast TMA over NVLink); the whole step replays as one CUDA graph"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -304,7 +303,7 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         shard = sharding.ViewShard()
-        if args.exchange in ("peer", "dma", "fused"):
+        if args.exchange in ("peer", "dma"):
             peer = sharding.PeerExchange(shard)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _lib.load()
@@ -349,105 +348,94 @@ def run_ours(args):
     ident = None if peer is None else peer.identity_index(R, dev)
     theta = torch.tensor([0.5], device=dev)
     big_events = []
-    main_stream = torch.cuda.current_stream()
-    side_stream = torch.cuda.Stream()
-    ev_b, ev_c = torch.cuda.Event(), [torch.cuda.Event() for _ in range(4)]
-    chunks, whole = [(0, R // 2), (R // 2, R)], [(0, R)]
-    # 32x32, d = 40: four CTAs per SM = 592 slots, 64 CTAs per row -> 9.25 rows per wave.  Whole waves per chunk, the
-    # smaller chunk first (its transfer is the exposed one): 27 rows = 3 waves, 37 rows = 4 waves (32 + 32 would be 4 + 4)
-    rpw = 148 * 4 / (HEADS * (32 * 32 // 128))
-    n_w = int(np.ceil(R / rpw))
-    r0 = int((n_w // 2) * rpw)
-    chunks32 = [(0, r0), (r0, R)] if 0 < r0 < R else chunks
-    runs32 = None
-    quarters = [(i * R // 4, (i + 1) * R // 4) for i in range(4)]
-    runs = runs_whole = runs_q = None
+    side_k, side_v = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_b = torch.cuda.Event()
+    ev_k, ev_v = [torch.cuda.Event() for _ in range(8)], [torch.cuda.Event() for _ in range(8)]
+
+    def parse_chunks(env, default):
+        spec = os.environ.get(env)
+        sizes = [int(x) for x in spec.split(",")] if spec else default
+        assert sum(sizes) == R and all(x > 0 for x in sizes) and len(sizes) <= 8, (env, sizes)
+        out, lo = [], 0
+        for n in sizes:
+            out.append((lo, lo + n))
+            lo += n
+        return out
+
+    # Row chunks of the copy-engine exchange (N > 1): the attention of chunk c runs under the transfer of chunk c + 1, so
+    # only the FIRST chunk's transfer is exposed -- it is the smallest; chunk sizes are whole waves of the attention grid
+    # where that matters (32x32, d = 40: four CTAs per SM = 592 slots, 64 CTAs per row -> 9.25 rows per wave; programmatic
+    # dependent launch lets a chunk's CTAs fill the tail of the chunk in front of it).
+    chunk_plan = {32: parse_chunks("CVD_BENCH_CHUNKS32", [9, 18, 37]), 16: parse_chunks("CVD_BENCH_CHUNKS16", [16, 16, 32])}
+    runs_of = None
     if shard is not None:
-        # contiguous runs of the partner map per chunk: (dst_lo, dst_hi, source rank, source row)
+        # contiguous runs of the partner map inside [lo, hi): (dst_lo, dst_hi, source rank, source row)
         ph = partner.cpu().numpy()
 
         def runs_of(lo, hi):
-            rr, a = [], lo
+            rr, a_ = [], lo
             for i in range(lo + 1, hi + 1):
-                if i == hi or ph[i] != ph[i - 1] + 1 or ph[i] // R != ph[a] // R:
-                    rr.append((a, i, int(ph[a]) // R, int(ph[a]) % R))
-                    a = i
+                if i == hi or ph[i] != ph[i - 1] + 1 or ph[i] // R != ph[a_] // R:
+                    rr.append((a_, i, int(ph[a_]) // R, int(ph[a_]) % R))
+                    a_ = i
             return rr
 
         partner_local = (partner % R).to(torch.int32)      # row inside the source rank's buffer
-        runs = [runs_of(lo, hi) for lo, hi in chunks]
-        runs_q = [runs_of(lo, hi) for lo, hi in quarters]
-        runs32 = [runs_of(lo, hi) for lo, hi in chunks32]
+        run_plan = {f: [runs_of(lo, hi) for lo, hi in ch] for f, ch in chunk_plan.items()}
         runs_whole = runs_of(0, R)
 
+    def timed_attn(record, *a):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.epi_attn_fwd(*a)
+            e1.record()
+            big_events.append((e0, e1, R / a[0].shape[0]))
+        else:
+            ops.epi_attn_fwd(*a)
+
     def value_step(record):
+        main_stream = torch.cuda.current_stream()
         for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
+            rec = record and feat == SHAPES[0][0]
             for q, k, vt, xk, xv in per_call:
                 rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
-                idx = partner
                 if shard is None:
-                    ks, vs = k, vt
+                    timed_attn(rec, q, k, vt, rowp, partner, HEADS, F_MAT_SIZE)
                 elif peer is None:            # baseline: NCCL all-gather of every rank's K and V^T
-                    ks, vs = shard.gather_rows(k), shard.gather_rows(vt)
-                elif args.exchange == "fused":
-                    # one cross-rank barrier (the partner's K / V^T of this call are complete), then ONE kernel: the
-                    # attention reads the partner tiles out of the peer's HBM itself (global partner rows)
-                    xk[1].barrier()
-                    if record and feat == SHAPES[0][0]:
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        ops.epi_attn_fwd_sharded(q, xk[2], xv[2], R, rowp, partner, HEADS, F_MAT_SIZE)
-                        e1.record()
-                        big_events.append((e0, e1, 1))
-                    else:
-                        ops.epi_attn_fwd_sharded(q, xk[2], xv[2], R, rowp, partner, HEADS, F_MAT_SIZE)
-                    continue
+                    timed_attn(rec, q, shard.gather_rows(k), shard.gather_rows(vt), rowp, partner, HEADS, F_MAT_SIZE)
                 elif args.exchange == "dma":
-                    # one cross-rank barrier, then the partner rows cross NVLink on the COPY ENGINES in two row chunks on a
-                    # side stream; the attention of chunk 0 runs under the transfer of chunk 1 (no SMs are spent on the pull)
-                    xk[1].barrier()
-                    if feat * feat <= 128 and len({rk for (_, _, rk, _) in runs_whole}) == 1:
-                        # one query tile per (row, head): the kernel reads the partner's K / V^T tiles straight out of
-                        # the peer's HBM (TMA over NVLink) -- every byte crosses once, no landing buffer, no copy launch.
-                        # (At larger grids the 2..8 query-tile CTAs of a (row, head) would each stream the partner rows
-                        # over the links; those shapes keep the copy-engine exchange below.)
+                    # one cross-rank barrier (the partner's K / V^T of this call are complete) ...
+                    sharding.barrier(xk[1])
+                    if feat * feat <= 64 and len({rk for (_, _, rk, _) in runs_whole}) == 1:
+                        # ... then, one query tile per (row, head): the kernel reads the partner's K / V^T tiles straight
+                        # out of the peer's HBM (unicast TMA over NVLink, plain loads at 4x4) -- every byte crosses once,
+                        # no landing buffer, no copy launch
                         src = runs_whole[0][2]
                         ops.epi_attn_fwd(q, xk[2][src], xv[2][src], rowp, partner_local, HEADS, F_MAT_SIZE)
                         continue
+                    # ... then the partner rows cross NVLink on the COPY ENGINES in row chunks (K and V^T on two side
+                    # streams), each chunk's attention running under the transfer of the next (no SMs spent on the pull)
                     ev_b.record(main_stream)
-                    with torch.cuda.stream(side_stream):
-                        side_stream.wait_event(ev_b)
-                        # small grids: one transfer, one attention launch (four 16-row chunks at 32x32 measured slower:
-                        # 6.28 vs 6.19 ms per step on 2 GPUs, the quarter-size attention grids lose more than the overlap gains)
-                        use = (chunks32 if feat == 32 else chunks) if feat >= 16 else whole
-                        for c, (lo, hi) in enumerate(use):
-                            for (dlo, dhi, src_rank, slo) in (runs_q[c] if use is quarters else (runs32[c] if use is chunks32 else (runs[c] if use is chunks else runs_whole))):
+                    side_k.wait_event(ev_b)
+                    side_v.wait_event(ev_b)
+                    for c, runs_c in enumerate(run_plan[feat]):
+                        with torch.cuda.stream(side_k):
+                            for (dlo, dhi, src_rank, slo) in runs_c:
                                 ld[0][dlo:dhi].copy_(xk[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
+                            ev_k[c].record(side_k)
+                        with torch.cuda.stream(side_v):
+                            for (dlo, dhi, src_rank, slo) in runs_c:
                                 ld[1][dlo:dhi].copy_(xv[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
-                            ev_c[c].record(side_stream)
-                    for c, (lo, hi) in enumerate(use):
-                        main_stream.wait_event(ev_c[c])
-                        if record and feat == SHAPES[0][0]:
-                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                            e0.record()
-                            ops.epi_attn_fwd(q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
-                            e1.record()
-                            big_events.append((e0, e1, R / (hi - lo)))
-                        else:
-                            ops.epi_attn_fwd(q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
-                    continue
+                            ev_v[c].record(side_v)
+                    for c, (lo, hi) in enumerate(chunk_plan[feat]):
+                        main_stream.wait_event(ev_k[c])
+                        main_stream.wait_event(ev_v[c])
+                        timed_attn(rec, q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
                 else:                         # one cross-rank barrier, then pull only the partner rows over NVLink (SM kernel)
                     ks = peer.pull(xk[0], xk[1], partner, ld[0], rows_per_src=R)
                     vs = ops.peer_gather_rows(xv[0], partner, ld[1], rows_per_src=R)
-                    idx = ident
-                if record and feat == SHAPES[0][0]:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    ops.epi_attn_fwd(q, ks, vs, rowp, idx, HEADS, F_MAT_SIZE)
-                    e1.record()
-                    big_events.append((e0, e1, 1))
-                else:
-                    ops.epi_attn_fwd(q, ks, vs, rowp, idx, HEADS, F_MAT_SIZE)
+                    timed_attn(rec, q, ks, vs, rowp, ident, HEADS, F_MAT_SIZE)
 
     def barrier():
         if world > 1:
@@ -457,18 +445,41 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         value_step(False)
     barrier()
+    # N > 1: the step is ~15 stream operations per call (barrier, event hand-offs, peer copies, chunk launches): issued
+    # eagerly the host cannot keep up with the GPU (round 1: SMs idle, 385 W).  The whole step is captured ONCE into a CUDA
+    # graph (device-side barriers, copy-engine transfers and kernels alike) and replayed; --no-graph times the eager loop.
+    graph = None
+    launches_per_step = None
+    if world > 1 and not args.no_graph:
+        l0 = ops.LAUNCHES
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            value_step(False)
+        launches_per_step = ops.LAUNCHES - l0
+        for _ in range(2):
+            graph.replay()
+        barrier()
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = ops.LAUNCHES
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        value_step(True)
+        if graph is not None:
+            graph.replay()
+        else:
+            value_step(True)
     t1.record()
     barrier()
-    launches = ops.LAUNCHES - launches0
+    launches = ops.LAUNCHES - launches0 if graph is None else launches_per_step * args.steps
     ms_value = t0.elapsed_time(t1) / args.steps
     clk = clocks.stop()
+    if graph is not None:       # the dominant kernel's launch time: two eager passes of the same step (events per launch)
+        for _ in range(2):
+            value_step(True)
+        barrier()
     big_ms = float(np.mean([a.elapsed_time(b) * n for a, b, n in big_events]))   # per full-R launch equivalent
 
     # ---------------- e2e: layer API with host buffers ----------------
@@ -585,18 +596,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "dma", "allgather"],
-                    help="N>1: read the partner rows inside the attention kernel (fused: TMA over NVLink, cluster multicast), "
-                         "pull them with our kernel (peer), with the copy engines in two row chunks overlapped with the "
-                         "attention (dma), or NCCL all-gather (baseline)")
+    ap.add_argument("--exchange", default="dma", choices=["peer", "dma", "allgather"],
+                    help="N>1: partner rows over NVLink by the copy engines in row chunks under the attention, small grids read "
+                         "in-kernel (dma, default), by our pull kernel (peer), or NCCL all-gather (baseline)")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: issue the step eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
     global EXCHANGE
     if args.exchange == "allgather":
         EXCHANGE = "NCCL all-gather"
     if args.exchange == "peer":
         EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
-    if args.exchange == "dma":
-        EXCHANGE = "NVLink copy engines, 2 row chunks under the attention; grids <= 8x8 read the peer's K/V^T in-kernel (TMA over NVLink)"
     if args.impl == "reference":
         run_reference(args)
     else:

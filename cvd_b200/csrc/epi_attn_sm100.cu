@@ -54,11 +54,11 @@ constexpr float kRescaleThreshold = 16.0f;  // lazy rescale: only when a score e
 
 // CL = CTAs per cluster.  CL > 1 ("multicast"): the CL query tiles of one (row, head) form a thread-block cluster and
 // share every K / V^T tile -- ONE TMA load per tile, issued by CTA (tile % CL), is delivered to the same shared-memory
-// stage of all CL CTAs (cp.async.bulk.tensor ... .multicast::cluster).  When K / V^T live in a PEER GPU's HBM (views
-// sharded across GPUs, the partner view's rows are remote) every byte then crosses NVLink once per (row, head) instead of
-// once per query tile, straight into shared memory, under the softmax of the tiles in front of it: the exchange of the
-// sharded layer is fused into the attention kernel.  A stage is refilled once ALL CL CTAs have consumed it: their MMA
-// commits arrive (multicast) on the stage's "empty" barrier of every CTA, which therefore counts CL arrivals.
+// stage of all CL CTAs (cp.async.bulk.tensor ... .multicast::cluster): K / V^T leave L2 once per (row, head) instead of
+// once per query tile.  A stage is refilled once ALL CL CTAs have consumed it: their MMA commits arrive (multicast) on
+// the stage's "empty" barrier of every CTA, which therefore counts CL arrivals.  Built for K / V^T in a PEER GPU's HBM
+// (views sharded across GPUs: every byte would cross NVLink once, under the softmax) -- but multicast TMA with a source
+// in peer memory never completes on this platform (see cluster_requested() below), so it is a LOCAL-memory variant.
 template <int D, int FEAT, int CL = 1>
 struct Cfg {
   static_assert(D % 8 == 0 && (D % 16 == 0 || D % 16 == 8), "head_dim must be a multiple of 8");
@@ -763,19 +763,36 @@ static int launch(const void* q, const KvSrc& src, const float* rowp, const int*
   return CVD_OK;
 }
 
-// CVD_ATTN_CLUSTER=1: use the cluster-multicast kernels for LOCAL K / V^T too (A/B measurements); sharded calls
-// (cvd_epi_attn_fwd_sharded) always use them where a (row, head) has more than one query tile.
-static bool cluster_local() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CVD_ATTN_CLUSTER");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+// Cluster-multicast kernels: used for K / V^T in LOCAL memory only.  MEASURED (round 2, 2 x B200, driver 580.159):
+// cp.async.bulk.tensor ... .multicast::cluster with a source in a PEER GPU's memory (NVLink mapping) never completes and
+// leaves the GPU unresponsive (the time-bounded mbarrier waits never get to trap), while the same kernel on local
+// copies of the same rows is bit-exact and unicast TMA reads of peer memory work.  So the cluster kernels
+// are opt-in (CVD_ATTN_CLUSTER=1 in the environment, read at every call) and, as a second line of defence, refused unless
+// every source is memory of the current device.
+static bool cluster_requested() {
+  const char* e = getenv("CVD_ATTN_CLUSTER");
+  return e != nullptr && e[0] == '1';
+}
+
+static bool all_sources_local(const KvSrc& src) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  for (int i = 0; i < src.n_src; ++i) {
+    const void* ptrs[2] = {src.k[i], src.v[i]};
+    for (const void* p : ptrs) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      if (a.type != cudaMemoryTypeDevice || a.device != dev) return false;
+    }
   }
-  return v == 1;
+  return true;
 }
 
 static int dispatch(const void* q, const KvSrc& src, const float* rowp, const int* partner, void* out, int R, int N, int heads,
-                    int head_dim, int n_partners, int feat, float S, float* dbg, float* lse, bool multicast, cudaStream_t st) {
+                    int head_dim, int n_partners, int feat, float S, float* dbg, float* lse, cudaStream_t st) {
   CVD_REQUIRE(q && partner && out, "cvd_epi_attn_fwd: null pointer");
   CVD_REQUIRE(src.n_src >= 1 && src.n_src <= kMaxSrc && src.rows_per_src > 0, "cvd_epi_attn_fwd: %d K/V sources of %d rows", src.n_src,
               src.rows_per_src);
@@ -791,7 +808,7 @@ static int dispatch(const void* q, const KvSrc& src, const float* rowp, const in
     const int rc = epi_attn_small_dispatch(q, src, rowp, partner, out, lse, R, heads, head_dim, n_partners, feat, S, st);
     if (rc != -1000) return rc;
   }
-  const bool mc = dbg == nullptr && (multicast || cluster_local());
+  const bool mc = dbg == nullptr && cluster_requested() && all_sources_local(src);
 #define CVD_CASE(D_, F_, CL_)                                                                                       \
   if (head_dim == D_ && feat == F_) {                                                                               \
     if (mc && CL_ > 1) return launch<D_, F_, CL_>(q, src, rowp, partner, out, R, heads, n_partners, S, dbg, lse, st); \
@@ -827,13 +844,12 @@ extern "C" int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, co
                                 float F_mat_size, cvd_stream_t stream) {
   CVD_REQUIRE(R_kv > 0, "cvd_epi_attn_fwd: R_kv=%d", R_kv);
   return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
-                              F_mat_size, nullptr, nullptr, false, (cudaStream_t)stream);
+                              F_mat_size, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // View-sharded form: K / V^T of the partner rows live in n_src buffers of rows_per_src rows each (the symmetric-memory
 // buffers of the GPUs of one NVSwitch box, passed as peer-mapped device pointers, own rank included); `partner` holds
-// GLOBAL rows.  The kernel reads the partner tiles straight out of the owning GPU's HBM; where a (row, head) has several
-// query tiles they form a thread-block cluster and every tile crosses NVLink once (TMA multicast).
+// GLOBAL rows.  The kernel reads the partner tiles straight out of the owning GPU's HBM (unicast TMA).
 extern "C" int cvd_epi_attn_fwd_sharded(const void* q, const void* const* k_srcs, const void* const* vt_srcs, int n_src,
                                         int rows_per_src, const float* rowp, const int* partner, void* out, int R, int N,
                                         int heads, int head_dim, int n_partners, int feat, float F_mat_size,
@@ -848,7 +864,7 @@ extern "C" int cvd_epi_attn_fwd_sharded(const void* q, const void* const* k_srcs
   s.n_src = n_src;
   s.rows_per_src = rows_per_src;
   return cvd::sm100::dispatch(q, s, rowp, partner, out, R, N, heads, head_dim, n_partners, feat, F_mat_size, nullptr, nullptr,
-                              true, (cudaStream_t)stream);
+                              (cudaStream_t)stream);
 }
 
 // Same as cvd_epi_attn_fwd, additionally writing the base-2 log-sum-exp of every (row, head, query) -- the statistic the
@@ -858,7 +874,7 @@ extern "C" int cvd_epi_attn_fwd_lse(const void* q, const void* k, const void* vt
                                     int feat, float F_mat_size, cvd_stream_t stream) {
   CVD_REQUIRE(lse != nullptr && R_kv > 0, "cvd_epi_attn_fwd_lse: null lse / R_kv=%d", R_kv);
   return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
-                              F_mat_size, nullptr, lse, false, (cudaStream_t)stream);
+                              F_mat_size, nullptr, lse, (cudaStream_t)stream);
 }
 
 // Bring-up aid: additionally dumps the raw Q K^T accumulator of key tile 0 of every CTA
@@ -868,5 +884,5 @@ extern "C" int cvd_epi_attn_fwd_debug(const void* q, const void* k, const void* 
                                       int n_partners, int feat, float F_mat_size, cvd_stream_t stream) {
   CVD_REQUIRE(R_kv > 0, "cvd_epi_attn_fwd_debug: R_kv=%d", R_kv);
   return cvd::sm100::dispatch(q, cvd::sm100::one_source(k, vt, R_kv), rowp, partner, out, R, N, heads, head_dim, n_partners, feat,
-                              F_mat_size, dbg_s, nullptr, false, (cudaStream_t)stream);
+                              F_mat_size, dbg_s, nullptr, (cudaStream_t)stream);
 }

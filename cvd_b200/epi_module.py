@@ -22,6 +22,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib, ops
+from .sharding import barrier as sharding_barrier
 
 FRAMES_PER_VIDEO = 16   # hard-coded by the reference (epi_module.py:316, attention_processor.py:631)
 
@@ -228,17 +229,17 @@ class EpiAttnProcessor(nn.Module):
             partner = self.partner_index(R, kv_index, x.device)
         w = attn._w
         q = F.linear(x, w.bf16("q", attn.to_q.weight))
-        if self.peer is not None and getattr(self.peer, "mode", "hidden") == "fused":
-            # view sharding, product path: K / V^T of the LOCAL rows go straight into symmetric memory (the GEMMs write
-            # them there); one cross-rank barrier; the attention kernel reads the partner rows' tiles out of the peers'
-            # HBM itself -- the exchange runs inside the kernel, under the softmax (cvd_epi_attn_fwd_sharded)
+        if self.peer is not None and getattr(self.peer, "mode", "hidden") == "fused" and N <= 64:
+            # view sharding, small latents (one query tile per (row, head)): K / V^T of the LOCAL rows go straight into
+            # symmetric memory (the GEMMs write them there); one cross-rank barrier; the attention kernel reads the partner
+            # rows' tiles out of the peers' HBM itself (cvd_epi_attn_fwd_sharded, unicast TMA over NVLink)
             DV = ops.dv_rows(d)
             k_loc, k_all, hk = self.peer.slot_views((R, N, C), torch.bfloat16, x.device)
             vt_loc, vt_all, _hv = self.peer.slot_views((R, H, DV, N), torch.bfloat16, x.device)
             torch.mm(x.view(R * N, C), w.bf16("k", attn.to_k.weight).t(), out=k_loc.view(R * N, C))   # == F.linear
             torch.matmul(attn.padded_v_weights(), x.transpose(1, 2), out=vt_loc.view(R, H * DV, N))
             vt_loc[:, :, d].fill_(1.0)
-            hk.barrier()
+            sharding_barrier(hk)
             o = ops.epi_attn_fwd_sharded(q, k_all, vt_all, R, epi_rowp, partner, H, attn.F_mat_size)
             if fix_firstframe:
                 o = self._fix_firstframe(attn, x, o, ff_group)

@@ -7,14 +7,14 @@ one exchange per epi-attention call and no other collective on the path.
 
 Exchange mechanisms:
 
-* ``PeerExchange`` in ``fused`` mode (product path): every rank projects K / V^T of its OWN rows into symmetric
-  memory; after one device-side cross-rank barrier the attention kernel itself reads the partner rows' tiles out of
-  the peers' HBM (``cvd_epi_attn_fwd_sharded``: TMA over NVLink, multicast to the query-tile CTAs of a (row, head)
-  cluster, so every byte crosses the links once and the transfer runs under the softmax).  No landing buffer, no copy
-  launch, no collective.
-* ``PeerExchange`` in ``hidden`` mode: the LayerNorm-ed hidden states live in symmetric memory; after the barrier every
-  rank PULLS exactly the rows its queries attend to with ``cvd_peer_gather_rows`` (our kernel, 16-byte loads over
-  NVLink) and projects K / V^T of those rows locally -- half the bytes, but a separate transfer in front of the GEMMs.
+* ``PeerExchange`` in ``hidden`` mode (product path): the LayerNorm-ed hidden states live in symmetric memory; after one
+  device-side cross-rank barrier every rank PULLS exactly the rows its queries attend to out of its peers' HBM with
+  ``cvd_peer_gather_rows`` (our kernel, 16-byte loads over NVLink) and projects K / V^T of those rows locally -- half
+  the bytes of exchanging K and V^T, R_local rows per call whatever the world size, no collective launch.
+* ``PeerExchange`` in ``fused`` mode: K / V^T of the local rows go to symmetric memory and, at latents <= 8x8, the
+  attention kernel reads the partner tiles out of the peers' HBM itself (``cvd_epi_attn_fwd_sharded``, unicast TMA over
+  NVLink: no landing buffer, no copy launch).  The kernel benchmark (``bench.py --gpus N``) uses the same in-kernel reads
+  for its small grids and the copy engines in row chunks under the attention for the large ones.
 * ``ViewShard.gather_rows`` (baseline, and the CPU/gloo test path): NCCL all-gather of every rank's
   rows; the attention kernel then indexes the gathered buffer with GLOBAL partner rows.
 
@@ -65,6 +65,16 @@ class ViewShard:
         return torch.cat(parts, dim=0)
 
 
+# A device-side cross-rank barrier spins on a flag the peer writes.  With a timeout the spin ends in a trap (a CUDA error
+# on the host) when a peer died or never arrives, instead of a kernel that occupies the GPU forever.
+BARRIER_TIMEOUT_MS = 30000
+
+
+def barrier(hdl, channel=0):
+    """Symmetric-memory barrier of ``hdl``'s group on the current stream, bounded by ``BARRIER_TIMEOUT_MS``."""
+    hdl.barrier(channel, BARRIER_TIMEOUT_MS)
+
+
 class PeerExchange:
     """Symmetric-memory workspaces (two slots per shape, used alternately) + peer row pull.
 
@@ -81,10 +91,13 @@ class PeerExchange:
         self._slots = {}
         self._views = {}
         self._arange = {}
-        # "fused": K / V^T of the local rows go to symmetric memory and the attention kernel reads the partner tiles out
-        # of the peers' HBM itself (cvd_epi_attn_fwd_sharded); "hidden": pull the partner rows of the LayerNorm-ed hidden
-        # states with cvd_peer_gather_rows and project them locally (half the bytes, but a separate, exposed transfer)
-        self.mode = "fused"
+        # "hidden" (default): pull the partner rows of the LayerNorm-ed hidden states with cvd_peer_gather_rows and
+        # project K / V^T of those rows locally (half the bytes of K + V^T).
+        # "fused": K / V^T of the local rows go to symmetric memory and, for latents <= 8x8 (one query tile per
+        # (row, head): every byte crosses NVLink once), the attention kernel reads the partner tiles out of the peers'
+        # HBM itself by unicast TMA; larger latents keep the hidden-row pull (several query-tile CTAs would each stream
+        # the partner rows, and multicast TMA from peer memory wedges the GPU: DESIGN.md section 6).
+        self.mode = "hidden"
 
     def alloc(self, shape, dtype, device):
         """One symmetric buffer (a collective call: every rank must allocate in the same order).
@@ -120,7 +133,7 @@ class PeerExchange:
         """out[r] = peers' row partner[r] (GLOBAL numbering) of an already written symmetric buffer,
         after a cross-rank barrier."""
         from . import ops
-        hdl.barrier()
+        barrier(hdl)
         return ops.peer_gather_rows(ptrs, partner, out, rows_per_src=rows_per_src)
 
     def exchange(self, x, partner):
@@ -129,7 +142,7 @@ class PeerExchange:
         from . import ops
         local, ptrs, hdl = self.slot(x.shape, x.dtype, x.device)
         local.copy_(x)
-        hdl.barrier()
+        barrier(hdl)
         out = torch.empty((partner.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
         return ops.peer_gather_rows(ptrs, partner, out, rows_per_src=x.shape[0])
 

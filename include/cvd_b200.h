@@ -82,16 +82,19 @@ int cvd_epi_attn_fwd(const void* q, const void* k, const void* vt, const float* 
                      const int* partner, void* out, int R, int R_kv, int N, int heads, int head_dim,
                      int n_partners, int feat, float F_mat_size, cvd_stream_t stream);
 
-/* ---- (e) view-sharded attention: the exchange fused into the kernel.
+/* ---- (e) view-sharded attention: K / V^T spread over several buffers, partner rows numbered globally.
  *      Replaces "all-gather K / V of the partner views, then attend" for attention_processor.py:573-583 when the views
  *      of a V-view run are sharded over the GPUs of one NVSwitch box (the reference has no multi-GPU inference).
  *      k_srcs / vt_srcs: n_src (1..8) device pointers, each a [rows_per_src, N, heads*head_dim] /
- *      [rows_per_src, heads, DV, N] buffer -- the symmetric-memory copies of every rank through their peer (NVLink)
+ *      [rows_per_src, heads, DV, N] buffer -- e.g. the symmetric-memory copies of every rank through their peer (NVLink)
  *      mappings, own rank included; `partner` holds GLOBAL rows: row p = source p / rows_per_src, local row
- *      p % rows_per_src.  Partner tiles are read straight out of the owning GPU's HBM by TMA; where a (row, head) has
- *      several query tiles (latents > 8x8) they form a thread-block cluster and each K / V^T tile crosses NVLink ONCE,
- *      multicast into the shared memory of all of them, under the softmax of the tiles in front of it.  The caller
- *      orders the call after the peers' writes (one cross-rank barrier per call).  Everything else as cvd_epi_attn_fwd. */
+ *      p % rows_per_src.  Partner tiles are read straight out of the owning buffer by TMA (unicast: measured safe over
+ *      NVLink; use it for latents <= 8x8, where a (row, head) has ONE query tile and every byte crosses once).  When all
+ *      sources are memory of the calling device and a (row, head) has several query tiles, those CTAs form a
+ *      thread-block cluster and each K / V^T tile is fetched once and multicast into the shared memory of all of them
+ *      (never for peer memory: multicast TMA from a peer mapping wedges the GPU on driver 580.159).
+ *      The caller orders the call after the peers' writes (one cross-rank barrier).  Everything else as
+ *      cvd_epi_attn_fwd. */
 int cvd_epi_attn_fwd_sharded(const void* q, const void* const* k_srcs, const void* const* vt_srcs, int n_src,
                              int rows_per_src, const float* rowp, const int* partner, void* out, int R, int N,
                              int heads, int head_dim, int n_partners, int feat, float F_mat_size,
