@@ -385,12 +385,14 @@ def run_ours(args):
         runs_whole = runs_of(0, R)
 
     def timed_attn(record, *a):
+        """One attention launch; with ``record`` its CUDA-event pair joins the event list of the current call (a call of
+        the dominant shape is one launch, or one launch per row chunk: the chunk times add up to the call)."""
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             ops.epi_attn_fwd(*a)
             e1.record()
-            big_events.append((e0, e1, R / a[0].shape[0]))
+            big_events[-1].append((e0, e1))
         else:
             ops.epi_attn_fwd(*a)
 
@@ -399,6 +401,8 @@ def run_ours(args):
         for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
             rec = record and feat == SHAPES[0][0]
             for q, k, vt, xk, xv in per_call:
+                if rec:
+                    big_events.append([])
                 rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
                 if shard is None:
                     timed_attn(rec, q, k, vt, rowp, partner, HEADS, F_MAT_SIZE)
@@ -452,14 +456,25 @@ def run_ours(args):
     launches_per_step = None
     if world > 1 and not args.no_graph:
         l0 = ops.LAUNCHES
-        cap = torch.cuda.Stream()
-        cap.wait_stream(torch.cuda.current_stream())
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=cap):
-            value_step(False)
-        launches_per_step = ops.LAUNCHES - l0
-        for _ in range(2):
-            graph.replay()
+        try:
+            cap = torch.cuda.Stream()
+            cap.wait_stream(torch.cuda.current_stream())
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=cap):
+                value_step(False)
+            launches_per_step = ops.LAUNCHES - l0
+            for _ in range(2):
+                g_.replay()
+            graph = g_
+        except Exception as exc:      # capture is an optimisation: fall back to the eager loop, and say so
+            print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed ({type(exc).__name__}: {exc}); "
+                  f"timing the eager loop", file=sys.stderr, flush=True)
+            graph = None
+        # every rank must take the same path (a graph replay and an eager step issue the same barriers, but keep it simple)
+        flag = torch.tensor([1 if graph is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            graph = None
         barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -480,7 +495,7 @@ def run_ours(args):
         for _ in range(2):
             value_step(True)
         barrier()
-    big_ms = float(np.mean([a.elapsed_time(b) * n for a, b, n in big_events]))   # per full-R launch equivalent
+    big_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in call) for call in big_events if call]))   # per call of R rows
 
     # ---------------- e2e: layer API with host buffers ----------------
     layers, hosts = [], []

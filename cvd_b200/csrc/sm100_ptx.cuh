@@ -31,24 +31,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait.  mbarrier.try_wait suspends the thread in hardware until the phase flips or its time hint (here 1 ms)
-// runs out, so the loop body runs rarely; a protocol bug (or a peer GPU that died) must end in a trap -- a CUDA error on
-// the host -- after a bounded TIME (4096 x 1 ms at most), never in a hung GPU.
-__device__ __forceinline__ bool mbar_try_wait_1ms(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(1000000u)
-      : "memory");
-  return ok != 0;
-}
+// Bounded wait.  mbarrier.try_wait blocks in hardware for a system-dependent time and wakes on the
+// phase flip, so the loop body runs rarely; a protocol bug must end in a trap (CUDA error on the
+// host), never in a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t tries = 0;
-  while (!mbar_try_wait_1ms(bar, parity)) {
-    if (++tries > 4096u) __trap();
+  while (!mbar_try_wait(bar, parity)) {
+    if (++tries > (1u << 22)) __trap();
   }
 }
 
