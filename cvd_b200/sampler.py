@@ -209,6 +209,106 @@ def sample_multiview(unet, latents, text_embeddings, schedule, num_inference_ste
     return latents
 
 
+def unit_table(V, cfg, accumulate_step):
+    """The independent UNet evaluations of ONE denoising update of the V-view loop
+    (pipeline_animation_epi_advanced.py:603-699): unit = (accumulate step a, view v, CFG branch c) -- every accumulate
+    step runs the UNet on the same latents under its own view pairing and the predictions are summed (:605,686-699).
+    Unit u = (a * V + v) * n_cfg + c.  Returns int arrays (a, v, c), each [A * V * n_cfg]."""
+    n_cfg = 2 if cfg else 1
+    u = np.arange(accumulate_step * V * n_cfg)
+    return u // (V * n_cfg), (u // n_cfg) % V, u % n_cfg
+
+
+def sample_multiview_units(unet, latents, text_embeddings, schedule, num_inference_steps=25, guidance_scale=8.5,
+                           aux_c2w=None, aux_K_mats=None, pose_embedding_features=None, multistep=1, accumulate_step=1,
+                           shard=None, rng=np.random, noise_fn=None, callback=None, kv_on_device=False, fundamental=None):
+    """The V-view loop of pipeline_animation_epi_advanced.py:596-705 partitioned by (view, CFG branch, accumulate step)
+    UNITS instead of whole views (BASELINE config 4: 6 views x 2 CFG x 2 accumulate steps = 24
+    units -> 3 per GPU on 8 GPUs; 6 views do not split over 8 ranks).
+
+    Every rank holds the latents of ALL V views (a few hundred KB) and evaluates the UNet on its own
+    ``U / world`` units in one batch: a unit is one video (16 rows) with one text embedding, the pose features of its
+    view and the F matrices of its accumulate step's pairing; its epi attention reads the rows of the unit
+    (a, partner_a(v), c), wherever that unit lives (global ``kv_index`` rows, exchanged by the layers exactly as for
+    view sharding).  The guidance combination and the accumulate sum are linear in the unit predictions, so every rank
+    adds ``w_c / A`` times its predictions into a [V, ...] buffer (w = 1 - g for the unconditional branch, g for the
+    conditional one) and ONE small all-reduce per update gives every rank the full noise prediction; DDIM update and
+    re-noise (drawn full-size from the identically seeded generator) then run replicated.
+
+    latents [V,c,f,h,w] (all views, identical on every rank); text_embeddings [2V,l,c] CFG-interleaved per view
+    (:556-560) or [V,l,c]; aux_c2w [V*f,4,4], aux_K_mats [V*f,3,3]; pose_embedding_features per level [V,C,f,h,w] (all
+    views).  ``fundamental(c2w, K, partner_rows) -> [V*f,3,3]``: defaults to the device kernel
+    (``ops.pairwise_fundamental``); the CPU tests pass the host fp64 path of ``cvd_b200.geometry``.
+    Returns the final latents of all V views."""
+    import torch.distributed as dist
+    cfg = guidance_scale > 1.0
+    world = 1 if shard is None else shard.world
+    rank = 0 if shard is None else shard.rank
+    V, f = latents.shape[0], latents.shape[2]
+    assert f == FRAMES, "the sync path hard-codes 16 frames per video (epi_module.py:316)"
+    assert V % 2 == 0, "views are paired: V must be even (pipeline_animation_epi_advanced.py:625)"
+    assert pose_embedding_features is not None, "the sync path is only active with pose features (:619)"
+    dev = latents.device
+    A = accumulate_step
+    ua, uv, uc = unit_table(V, cfg, A)
+    U = ua.shape[0]
+    if U % world != 0:
+        raise ValueError(f"{U} (accumulate, view, cfg) units do not split over {world} ranks")
+    U_loc = U // world
+    mine = slice(rank * U_loc, (rank + 1) * U_loc)
+    la, lv, lc = ua[mine], uv[mine], uc[mine]
+    n_cfg = 2 if cfg else 1
+    timesteps = schedule.set_timesteps(num_inference_steps)
+    c2w = torch.as_tensor(np.asarray(aux_c2w.cpu() if torch.is_tensor(aux_c2w) else aux_c2w), dtype=torch.float64).reshape(-1, 4, 4)
+    Kd = torch.as_tensor(np.asarray(aux_K_mats.cpu() if torch.is_tensor(aux_K_mats) else aux_K_mats), dtype=torch.float64).reshape(-1, 3, 3)
+    assert c2w.shape[0] == V * f
+    if fundamental is None:
+        from . import ops
+        c2w, Kd = c2w.to(dev), Kd.to(dev)
+
+        def fundamental(c2w_, K_, partner_rows):
+            return ops.pairwise_fundamental(c2w_, K_, torch.from_numpy(partner_rows.astype(np.int32)).to(dev))
+    lv_t = torch.as_tensor(lv, device=dev, dtype=torch.long)
+    text_loc = text_embeddings[torch.as_tensor(lv * n_cfg + lc, device=text_embeddings.device, dtype=torch.long)]
+    pose_loc = [x[lv_t.to(x.device)] for x in pose_embedding_features]
+    weight = torch.as_tensor(np.where(lc == 1, guidance_scale, 1.0 - guidance_scale) if cfg else np.ones(U_loc),
+                             device=dev, dtype=latents.dtype).view(U_loc, 1, 1, 1, 1)
+    frames = np.arange(f)
+
+    for i, t in enumerate(timesteps):
+        n_rep = multistep if i != len(timesteps) - 1 else 1
+        for mt in range(n_rep):
+            # one pairing per accumulate step, drawn in the reference's order (:621-633 inside the accumulate loop)
+            F_rows, kv_rows = [], []
+            pair = [draw_view_pairing(V, f, rng)[0] for _ in range(A)]               # video_id [V*f] per accumulate step
+            F_acc = [fundamental(c2w, Kd, pair[a_]).reshape(V, f, 3, 3) for a_ in sorted(set(la.tolist()))]
+            F_by_a = dict(zip(sorted(set(la.tolist())), F_acc))
+            for a_, v_, c_ in zip(la, lv, lc):
+                F_rows.append(F_by_a[int(a_)][int(v_)])
+                pv = pair[int(a_)][int(v_) * f] // f                                   # partner view under pairing a
+                pu = (int(a_) * V + int(pv)) * n_cfg + int(c_)                         # partner unit: same a, same c
+                kv_rows.append(pu * f + frames)
+            Fm = torch.stack(F_rows).to(device=dev).type_as(latents)
+            kv = np.concatenate(kv_rows)                                             # GLOBAL rows, this rank's units
+            if kv_on_device:
+                kv = torch.from_numpy(np.ascontiguousarray(kv).astype(np.int32)).to(dev, non_blocking=True)
+            x_in = schedule.scale_model_input(latents[lv_t], t)
+            pred = _sample_of(unet(x_in, t, F_mats=[Fm, kv], encoder_hidden_states=text_loc,
+                                   pose_embedding_features=pose_loc)).to(latents.dtype)
+            noise_pred = torch.zeros_like(latents)
+            noise_pred.index_add_(0, lv_t, pred * weight)
+            if world > 1:
+                dist.all_reduce(noise_pred, group=shard.group)
+            latents = schedule.step(noise_pred / A, t, latents)
+            if mt != n_rep - 1:
+                shape = tuple(latents.shape)
+                noise = torch.randn(shape, device=dev, dtype=latents.dtype) if noise_fn is None else noise_fn(shape)
+                latents = schedule.renoise(latents, t, noise)
+        if callback is not None:
+            callback(i, t, latents)
+    return latents
+
+
 def install_sharding(module, shard, peer=None):
     """Point every EpiAttnProcessor under ``module`` at the view shard (and the NVLink peer exchange)."""
     from .epi_module import EpiAttnProcessor

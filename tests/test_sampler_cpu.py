@@ -234,3 +234,87 @@ def test_ddim_schedule_against_independent_fp64_fixture():
         out = sch.renoise(torch.from_numpy(g["renoise_in"]).float(), int(t), torch.from_numpy(g["renoise_noise"]).float())
         ref = torch.from_numpy(g["renoise_out"][j]).float()
         assert float((out - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+# ---- BASELINE config 4 partitioning: (view, cfg, accumulate step) units over 8 ranks ------------------------------------
+def _unit_inputs(V):
+    g = torch.Generator().manual_seed(17)
+    lat = torch.randn(V, 4, 16, 4, 4, generator=g)
+    text = torch.randn(2 * V, 7, 12, generator=g)                     # [U, C] per view, every view its own pair
+    poses = [torch.randn(V, 8, 16, 4, 4, generator=g)]
+    c2w, K = sampler.multiview_cameras(V, 16, "upper_hemi" if V == 6 else "circle", 0.5, 256)
+    return lat, text, poses, c2w, K
+
+
+def _host_fundamental(c2w, K, partner_rows):
+    from cvd_b200 import geometry
+    return geometry.pairwise_fundamental_matrices(c2w.numpy(), K.numpy(), partner_rows[::16] // 16)
+
+
+def _noise_stream(seed):
+    g = torch.Generator().manual_seed(seed)
+    return lambda shape: torch.randn(tuple(shape), generator=g)
+
+
+def _run_units(V, shard, unet, seed, steps=3, multistep=2, acc=2, kv_on_device=False):
+    lat, text, poses, c2w, K = _unit_inputs(V)
+    np.random.seed(seed)
+    return sampler.sample_multiview_units(unet, lat.clone(), text, sampler.DDIMSchedule(), steps, 8.5, aux_c2w=c2w,
+                                          aux_K_mats=K, pose_embedding_features=poses, multistep=multistep,
+                                          accumulate_step=acc, shard=shard, noise_fn=_noise_stream(seed),
+                                          fundamental=_host_fundamental, kv_on_device=kv_on_device)
+
+
+def test_unit_table_config4():
+    """6 views x 2 CFG branches x 2 accumulate steps = 24 units -> 3 per GPU on 8 GPUs."""
+    a, v, c = sampler.unit_table(6, True, 2)
+    assert a.shape[0] == 24 and 24 % 8 == 0
+    assert sorted(zip(a.tolist(), v.tolist(), c.tolist())) == [(x, y, z) for x in range(2) for y in range(6) for z in range(2)]
+    a1, v1, c1 = sampler.unit_table(4, False, 1)
+    assert v1.tolist() == [0, 1, 2, 3] and set(c1.tolist()) == {0} and set(a1.tolist()) == {0}
+
+
+@pytest.mark.parametrize("V,acc", [(6, 2), (4, 1)])
+def test_unit_loop_single_process_equals_oracle_loop(V, acc):
+    """The unit-partitioned loop on ONE process (all 2*V*acc units in one UNet batch) == the oracle restatement of the
+    reference loop (accumulate steps run one after the other, predictions summed): same pairing draws (numpy global RNG),
+    same F, same CFG combination, same re-noise."""
+    lat, text, poses, c2w, K = _unit_inputs(V)
+    np.random.seed(31)
+    ref = SO.sample_multiview(ToyUNet(), lat.clone(), text, 3, 8.5, c2w, K, poses, multistep=2, accumulate=acc,
+                              noise_fn=_noise_stream(31))
+    u = ToyUNet()
+    got = _run_units(V, None, u, 31, acc=acc)
+    assert len(u.calls) == 5 and u.calls[0][1] == (2 * V * acc, 16, 3, 3)        # (2*2 + 1) updates, ONE UNet batch each
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), float((got - ref).abs().max())
+
+
+def _unit_worker(rank, world, port, V, acc, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cvd_b200.sharding import ViewShard
+        shard = ViewShard()
+        unet = ToyUNet(gather=shard.gather_rows)
+        out = _run_units(V, shard, unet, 31, acc=acc)
+        assert unet.calls[0][1] == (2 * V * acc // world, 16, 3, 3)
+        ret[rank] = out.numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("V,acc,world", [(6, 2, 8), (4, 1, 4)])
+def test_unit_loop_sharded_equals_single_process(V, acc, world):
+    """BASELINE config 4 (6 views, 2 accumulate steps, 8 ranks: 3 units per rank) and config 3 (4 views on 4 ranks: one
+    view x both CFG branches per rank) over gloo: partner rows through the layers' exchange, ONE all-reduce of the
+    weighted predictions per update, replicated DDIM / re-noise -> every rank ends with the latents of the
+    single-process loop."""
+    ref = _run_units(V, None, ToyUNet(), 31, acc=acc)
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_unit_worker, args=(world, port, V, acc, ret), nprocs=world, join=True)
+    for r in range(world):
+        got = torch.from_numpy(ret[r])
+        assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), (r, float((got - ref).abs().max()))
