@@ -253,6 +253,39 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
             ms_eager = e2.elapsed_time(e3) / steps
     assert torch.isfinite(out).all()
     by_views = None
+    if world > 1 and 24 % world == 0:
+        # BASELINE config 4: 6-view 'upper_hemi' generation, accumulate_step 2 -> 6 x 2 (cfg) x 2 (acc) = 24 independent
+        # UNet evaluations per update, sharded as UNITS (24 / world per GPU: 3 on 8 GPUs), partner rows through the layers'
+        # NVLink exchange, one small all-reduce of the weighted predictions per update (sampler.sample_multiview_units).
+        # Guarded: a failure is reported in the line (every rank runs the same host logic, so it fails on all or none).
+        try:
+            V6 = 6
+            g6 = torch.Generator(device=dev).manual_seed(43)
+            lat6 = torch.randn(V6, 4, 16, 32, 32, device=dev, generator=g6)
+            poses6 = [torch.randn(V6, c, 16, 32 >> i, 32 >> i, device=dev, generator=g6) for i, c in enumerate(sync_unet.CHANNELS)]
+            text6 = torch.randn(2, 77, 768, device=dev, generator=g6).repeat(V6, 1, 1)
+            c2w6, K6 = sampler.multiview_cameras(V6, 16, "upper_hemi", 0.5, 256)
+
+            def run6(n):
+                return sampler.sample_multiview_units(net, lat6, text6, sch, n, 8.5, aux_c2w=c2w6, aux_K_mats=K6,
+                                                      pose_embedding_features=poses6, accumulate_step=2, shard=shard)
+            with torch.no_grad():
+                run6(2)
+                torch.distributed.barrier()
+                torch.cuda.synchronize()
+                a6, b6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a6.record()
+                o6 = run6(steps)
+                b6.record()
+                torch.distributed.barrier()
+                torch.cuda.synchronize()
+            ms6 = torch.tensor([a6.elapsed_time(b6) / steps], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(ms6, op=torch.distributed.ReduceOp.MAX)
+            by_views = {"config4": {"steps_per_s": 1e3 / float(ms6.item()), "views": V6, "accumulate_step": 2,
+                                    "units_per_gpu": 24 // world, "rig": "upper_hemi", "finite": bool(torch.isfinite(o6).all()),
+                                    "loop": "sampler.sample_multiview_units ((view, cfg, acc) units sharded, one all-reduce per update)"}}
+        except Exception as exc:
+            by_views = {"config4": {"error": f"{type(exc).__name__}: {exc}"}}
     if world == 1:
         # BASELINE metric "denoise steps/s at 2/4/6 views": the V-view loop (fresh pairing, device F recompute and kv_index
         # gather per UNet call) with all V views on this one GPU (R = 32 V rows), multistep = 1
@@ -278,6 +311,72 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
             by_views[str(Vn)] = {"steps_per_s": 1e3 / (a.elapsed_time(b) / steps), "rows": 32 * Vn,
                                  "launch": "one CUDA graph per UNet forward (kv_index on the device)", "rig": rig}
     return e0.elapsed_time(e1) / steps, V, ms_eager, by_views
+
+
+def extras_single_gpu(dev, peak_bw, F_rows):
+    """Two more measurements for the N = 1 line, each guarded (a failure is reported in the line, never fatal):
+
+    roofline_glue : achieved HBM GB/s of every glue kernel (GroupNorm + layout, LayerNorm, residual, GEGLU, temporal
+                    attention, ...) at the config-2 shapes against the measured copy bandwidth (scripts/profile_glue.py).
+    reference_gpu : the reference's own PyTorch GPU path (oracle/gpu_reference.py: fp32 eager -- dense bias per call, NaN
+                    check with its host sync, mask x 8 heads, SDPA -- and the same under bf16 autocast) for ONE
+                    EpiSelfAttention.forward per shape on device tensors, beside the product layer on the same inputs."""
+    glue_rows = ref_gpu = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import profile_glue
+        rows = profile_glue.measure(dev, peak_bw)
+        glue_rows = [{"kernel": r["kernel"], "shape": r["shape"], "us": round(r["us"], 2), "gbs": round(r["gbs"], 1),
+                      "frac": round(r["frac"], 4)} for r in rows]
+    except Exception as exc:
+        glue_rows = {"error": f"{type(exc).__name__}: {exc}"}
+    try:
+        import cvd_b200
+        import golden_inputs as gi
+        from oracle.gpu_reference import reference_gpu_layer
+
+        def timed(fn, iters, warm):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / iters, out
+
+        per_shape, tot = [], {"fp32": 0.0, "bf16_autocast": 0.0, "ours": 0.0}
+        with torch.no_grad():
+            for feat, C in SHAPES:
+                sd = gi.attn_state_dict(C, 10 + feat)
+                sd_dev = {k: v.to(dev) for k, v in sd.items()}
+                x = torch.randn(R_PER_GPU, feat * feat, C, device=dev, generator=torch.Generator(device=dev).manual_seed(feat))
+                attn = cvd_b200.EpiSelfAttention(attention_mode="Epi_Self", cross_attention_dim=None, query_dim=C, heads=HEADS,
+                                                 dim_head=C // HEADS, epi_position_encoding=True,
+                                                 epi_position_encoding_feat_max_size=64,
+                                                 epi_position_encoding_F_mat_size=F_MAT_SIZE, epi_rand_slope_ff=False)
+                attn.load_state_dict(sd, strict=False)
+                attn = attn.to(dev).eval()
+                t32, y32 = timed(lambda: reference_gpu_layer(x, sd_dev, HEADS, F_rows, F_MAT_SIZE), 3, 1)
+                t16, y16 = timed(lambda: reference_gpu_layer(x, sd_dev, HEADS, F_rows, F_MAT_SIZE, autocast=True), 3, 1)
+                tour, your = timed(lambda: attn(x, F_mats=F_rows)[0], 10, 3)
+                err = float((your.double() - y32.double()).norm() / y32.double().norm())
+                per_shape.append({"N": feat * feat, "C": C, "reference_fp32_ms": t32, "reference_bf16_autocast_ms": t16,
+                                  "ours_ms": tour, "rel_l2_vs_fp32": err})
+                tot["fp32"] += t32
+                tot["bf16_autocast"] += t16
+                tot["ours"] += tour
+                del attn, sd_dev, x, y32, y16, your
+                torch.cuda.empty_cache()
+        ref_gpu = {"what": "EpiSelfAttention.forward, R=64, device tensors, one call per shape (the reference's PyTorch GPU "
+                           "path = oracle/gpu_reference.py: dense bias + mask x 8 heads + SDPA)",
+                   "per_shape": per_shape, "sum_ms": tot,
+                   "speedup_vs_fp32": tot["fp32"] / tot["ours"], "speedup_vs_bf16_autocast": tot["bf16_autocast"] / tot["ours"]}
+    except Exception as exc:
+        ref_gpu = {"error": f"{type(exc).__name__}: {exc}"}
+    return glue_rows, ref_gpu
 
 
 # ------------------------------------------------------------------------------------------
@@ -362,11 +461,15 @@ def run_ours(args):
             lo += n
         return out
 
-    # Row chunks of the copy-engine exchange (N > 1): the attention of chunk c runs under the transfer of chunk c + 1, so
-    # only the FIRST chunk's transfer is exposed -- it is the smallest; chunk sizes are whole waves of the attention grid
-    # where that matters (32x32, d = 40: four CTAs per SM = 592 slots, 64 CTAs per row -> 9.25 rows per wave; programmatic
-    # dependent launch lets a chunk's CTAs fill the tail of the chunk in front of it).
-    chunk_plan = {32: parse_chunks("CVD_BENCH_CHUNKS32", [9, 18, 37]), 16: parse_chunks("CVD_BENCH_CHUNKS16", [16, 16, 32])}
+    # Row chunks of the copy-engine exchange (N > 1): the attention of chunk c runs under the transfer of chunk c + 1.
+    # Chunk sizes are whole waves of the attention grid (a launch rounds up to waves: its CTAs wait for the launch in front
+    # to complete, programmatic dependent launch only hides their prologue):
+    #   32x32, d = 40: 592 CTA slots (four per SM), 64 CTAs per row -> 9.25 rows per wave.  Attention-bound (214 us of
+    #     attention against 136 us of transfer): only the FIRST chunk's transfer is exposed, so it is the smallest:
+    #     9 | 18 | 37 rows = 1 | 2 | 4 waves, transfers of 19 | 38 | 79 us under attention of 31 | 62 | 124 us.
+    #   16x16, d = 80: 296 slots, 16 CTAs per row -> 18.5 rows per wave.  Transfer-bound (68 us against 36 us): the step
+    #     ends one chunk of attention after the LAST byte lands, so the last chunks are the small ones: 28 | 18 | 18.
+    chunk_plan = {32: parse_chunks("CVD_BENCH_CHUNKS32", [9, 18, 37]), 16: parse_chunks("CVD_BENCH_CHUNKS16", [28, 18, 18])}
     runs_of = None
     if shard is not None:
         # contiguous runs of the partner map inside [lo, hi): (dst_lo, dst_hi, source rank, source row)
@@ -497,6 +600,31 @@ def run_ours(args):
         barrier()
     big_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in call) for call in big_events if call]))   # per call of R rows
 
+    # every attention shape on its own (N = 1): the 10 calls of the shape back to back on their distinct buffers
+    by_shape = None
+    if world == 1 and not args.no_extras:
+        try:
+            by_shape = []
+            for (feat, C), per_call in zip(SHAPES, bufs):
+                rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
+                for q, k, vt, _xk, _xv in per_call[:2]:
+                    ops.epi_attn_fwd(q, k, vt, rowp, partner, HEADS, F_MAT_SIZE)
+                torch.cuda.synchronize()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for q, k, vt, _xk, _xv in per_call:
+                    ops.epi_attn_fwd(q, k, vt, rowp, partner, HEADS, F_MAT_SIZE)
+                b_.record()
+                torch.cuda.synchronize()
+                us = a_.elapsed_time(b_) / len(per_call) * 1e3
+                fl = 4.0 * R * (feat * feat) ** 2 * C
+                by_shape.append({"N": feat * feat, "C": C, "head_dim": C // HEADS, "us_per_launch": us,
+                                 "tflops": fl / us / 1e6, "frac": fl / us / 1e6 / peak_tf,
+                                 "kernel": "epi_attn_small_kernel (mma.sync, warp-level)" if feat <= 4 else
+                                           f"epi_attn_fwd_kernel<{C // HEADS},{feat}> (tcgen05)"})
+        except Exception as exc:
+            by_shape = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---------------- e2e: layer API with host buffers ----------------
     layers, hosts = [], []
     for feat, C in SHAPES:
@@ -559,6 +687,10 @@ def run_ours(args):
     torch.cuda.empty_cache()
     ms_denoise, views, ms_eager, by_views = (None, 0, None, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
 
+    glue_rows = ref_gpu = None
+    if world == 1 and not args.no_extras:
+        glue_rows, ref_gpu = extras_single_gpu(dev, peak_bw, F_rows)
+
     # max over ranks
     if world > 1:
         tt = torch.tensor([ms_value, ms_e2e, big_ms, ms_denoise or 0.0], device=dev, dtype=torch.float64)
@@ -590,6 +722,12 @@ def run_ours(args):
             "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                              "sample": f"oracle EpiSelfAttention.forward, 1 call per shape ({cb_flops / 1e9:.1f} GFLOP), best of 2"},
         }
+        if by_shape is not None:
+            line["roofline_by_shape"] = by_shape
+        if glue_rows is not None:
+            line["roofline_glue"] = glue_rows
+        if ref_gpu is not None:
+            line["reference_gpu"] = ref_gpu
         if ms_denoise is not None:
             line["denoise"] = {"steps_per_s": 1e3 / ms_denoise, "ms_per_step": ms_denoise, "views": views,
                                "rows_per_gpu": R_PER_GPU, "guidance_scale": 8.5,
@@ -611,6 +749,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip roofline_by_shape / roofline_glue / reference_gpu (N = 1 only; a few seconds)")
     ap.add_argument("--exchange", default="dma", choices=["peer", "dma", "allgather"],
                     help="N>1: partner rows over NVLink by the copy engines in row chunks under the attention, small grids read "
                          "in-kernel (dma, default), by our pull kernel (peer), or NCCL all-gather (baseline)")

@@ -10,7 +10,6 @@ import os
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
 import golden_inputs as gi
 from gpu_util import rel_l2
@@ -38,25 +37,7 @@ def timed(fn, iters, warm=2):
     return e0.elapsed_time(e1) / iters, out
 
 
-def reference_gpu_layer(x, sd, heads, F_mats, S=256):
-    """EpiSelfAttention.forward as the reference runs it on a GPU (fp32): get_attn_map -> NaN scrub -> mask replicated
-    over the heads (prepare_attention_mask, attention_processor.py:585-587) -> to_q/k/v -> SDPA(mask) -> to_out."""
-    from oracle import epi_oracle as O
-    R, N, C = x.shape
-    with torch.device(x.device):
-        bias = O.epi_bias(F_mats, int(N ** 0.5), S)                       # [R,N,N] fp32, horizontal first-frame rule
-    if bool(torch.isnan(bias).any()):                                     # the reference's host sync (:404)
-        bias = torch.nan_to_num(bias)
-    mask = bias.repeat_interleave(heads, dim=0).view(R, heads, N, N)      # x8 copy, as prepare_attention_mask does
-    idx = torch.cat([torch.arange(R // 2, R), torch.arange(0, R // 2)]).to(x.device)
-    enc = x[idx]
-    d = C // heads
-    q = F.linear(x, sd["to_q.weight"]).view(R, N, heads, d).transpose(1, 2)
-    k = F.linear(enc, sd["to_k.weight"]).view(R, N, heads, d).transpose(1, 2)
-    v = F.linear(enc, sd["to_v.weight"]).view(R, N, heads, d).transpose(1, 2)
-    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0, is_causal=False)
-    o = o.transpose(1, 2).reshape(R, N, C)
-    return F.linear(o, sd["to_out.0.weight"], sd["to_out.0.bias"])
+from oracle.gpu_reference import reference_gpu_layer  # noqa: E402
 
 
 def test_layer_vs_reference_gpu_path(dev):
