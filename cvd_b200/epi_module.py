@@ -104,6 +104,33 @@ class FeedForward(nn.Module):
         return F.linear(ops.geglu(hg), w.bf16("w2", self.net[2].weight))
 
 
+def pseudo_line_matrices(slopes):
+    """``get_pseudo_F_coords(random_slope=True)`` (epi_module.py:331-339) as per-row matrices: the line through the query
+    pixel with direction angle ``slopes[r]`` is (cos, sin, -(cos x + sin y)) = M_r (x, y, 1)^T.  [R] -> fp32 [R,3,3]."""
+    c, s = torch.cos(slopes.float()), torch.sin(slopes.float())
+    M = torch.zeros(slopes.shape[0], 3, 3, device=slopes.device, dtype=torch.float32)
+    M[:, 0, 2], M[:, 1, 2], M[:, 2, 0], M[:, 2, 1] = c, s, -c, -s
+    return M
+
+
+def homography_line_matrices(H_mats, slopes, F_mat_size):
+    """The H_mats branch of ``get_attn_map`` (epi_module.py:301-310) as per-row line matrices.  The reference warps every
+    query pixel by the row's homography about the image centre c0 = (S - 1) / 2, (U, V, W) = H (x - c0, y - c0, 1) with
+    W += 1e-6, (u, v) = (U / W + c0, V / W + c0), and draws the pseudo line (cos, sin, -(cos u + sin v)) through the
+    WARPED point.  Point-line distances are invariant under l -> W l, and
+        W l_q = (cos W, sin W, -(cos (U + c0 W) + sin (V + c0 W)))
+    is linear in (x, y, 1): the whole branch is the row table of an effective matrix
+        M_r = [cos h3'; sin h3'; -(cos h1 + sin h2 + (cos + sin) c0 h3')] T,  h3' = h3 + (0, 0, 1e-6),  T = shift by -c0,
+    and runs through the same kernels as the F_mats branch.  H_mats [R,3,3], slopes [R] -> fp32 [R,3,3]."""
+    H = H_mats.float()
+    c0 = (F_mat_size - 1) / 2
+    c, s = torch.cos(slopes.float())[:, None], torch.sin(slopes.float())[:, None]
+    h3 = H[:, 2] + torch.tensor([0.0, 0.0, 1e-6], device=H.device)
+    rows = torch.stack([c * h3, s * h3, -(c * H[:, 0] + s * H[:, 1] + (c + s) * c0 * h3)], dim=1)
+    T = torch.tensor([[1.0, 0.0, -c0], [0.0, 1.0, -c0], [0.0, 0.0, 1.0]], device=H.device)
+    return rows @ T
+
+
 class EpiEncoding(nn.Module):
     """epi_module.py:271-346.  Keeps the reference's persistent ``coords`` buffer (state_dict
     key ``pos_encoder.coords``); the geometry itself is evaluated on the device."""
@@ -116,14 +143,29 @@ class EpiEncoding(nn.Module):
         cx, cy = torch.meshgrid(coords, coords, indexing="xy")
         self.register_buffer("coords", torch.stack([cx, cy, cx * 0 + 1], dim=-1))
         self.theta_override = None   # tests inject the first-frame slope here (device fp32 [1])
+        self.slope_override = None   # ... and the per-row slopes of the H_mats / F_mats=None branches here (fp32 [rows])
 
-    def row_params(self, x, F_mats, pixel_band=3, decay_alpha=3):
-        """Row table [rows,12] for the fused kernel.  Consumes the global RNG exactly like the
-        reference: one ``torch.rand([1], device=...)`` per call when rand_slope is on
-        (epi_module.py:316,335)."""
+    def row_params(self, x, F_mats=None, H_mats=None, pixel_band=3, decay_alpha=3):
+        """Row table [rows,12] for the fused kernel, all three branches of ``get_attn_map`` (epi_module.py:301-320).
+        Consumes the global RNG exactly like the reference: F_mats branch, one ``torch.rand([1], device=...)`` per call
+        when rand_slope is on (:316,335); H_mats and F_mats=None branches, one ``torch.rand([rows], device=...)``
+        (pseudo lines with a random slope per row, :310,320) -- those two reduce to effective line matrices
+        (:func:`homography_line_matrices`, :func:`pseudo_line_matrices`) and need no first-frame rule."""
         feat = int(x.shape[1] ** 0.5)
         if feat * feat != x.shape[1]:
             raise ValueError(f"EpiEncoding needs a square latent, got {x.shape[1]} tokens (epi_module.py:294)")
+        if H_mats is not None or F_mats is None:
+            rows = H_mats.shape[0] if H_mats is not None else x.shape[0]
+            if self.slope_override is not None:
+                slopes = self.slope_override.to(device=x.device, dtype=torch.float32).reshape(rows)
+            else:
+                slopes = torch.rand([rows], device=x.device) * math.pi
+            if H_mats is not None:
+                M = homography_line_matrices(H_mats.detach().to(x.device), slopes, self.F_mat_size)
+            else:
+                M = pseudo_line_matrices(slopes)
+            return ops.epi_row_params(M.contiguous(), feat, self.F_mat_size, None, _lib.FF_NONE, pixel_band, decay_alpha,
+                                      FRAMES_PER_VIDEO)
         Fm = F_mats.detach().to(device=x.device, dtype=torch.float32).contiguous()
         theta, rule = None, _lib.FF_HORIZONTAL
         if self.rand_slope_on_first_frame:
@@ -136,10 +178,8 @@ class EpiEncoding(nn.Module):
 
     def get_attn_map(self, x, F_mats=None, H_mats=None, pixel_band=3, decay_alpha=3):
         """Dense bias [rows, N, N] -- parity/debug API only; the product path never calls it."""
-        if H_mats is not None or F_mats is None:
-            raise NotImplementedError("only the F_mats branch of get_attn_map is built (epi_module.py:311-316)")
         feat = int(x.shape[1] ** 0.5)
-        return ops.epi_bias_dense(self.row_params(x, F_mats, pixel_band, decay_alpha), feat, self.F_mat_size)
+        return ops.epi_bias_dense(self.row_params(x, F_mats, H_mats, pixel_band, decay_alpha), feat, self.F_mat_size)
 
 
 class _Aux(dict):
@@ -340,8 +380,6 @@ class EpiSelfAttention(nn.Module):
 
     def attend(self, hidden_states, F_mats=None, H_mats=None, **kw):
         """Core of forward: returns (y bf16 [R',N,C] *without* the to_out bias, aux)."""
-        if H_mats is not None:
-            raise NotImplementedError("the H_mats (homography) branch is training-only (epi_module.py:301-310) and is not built")
         assert isinstance(self.processor, EpiAttnProcessor)   # epi_module.py:423
         kw = {k: v for k, v in kw.items() if k not in ("pose_feature", "sync_lora_scale")}
         scale = kw.pop("scale", None)
@@ -349,9 +387,7 @@ class EpiSelfAttention(nn.Module):
         R, N, _ = hidden_states.shape
         rowp = None
         if self.pos_encoder is not None and not self.epi_no_attention_mask:
-            if Fm is None:
-                raise NotImplementedError("F_mats=None (random pseudo lines on every row, epi_module.py:317-320) is not built")
-            rowp = self.pos_encoder.row_params(hidden_states, Fm)
+            rowp = self.pos_encoder.row_params(hidden_states, Fm, H_mats)     # all three branches (epi_module.py:301-320)
             assert rowp.shape[0] % R == 0   # epi_module.py:399
         n_partners = 1 if rowp is None else rowp.shape[0] // R
         if self.reference_chunk_quirk and rowp is not None and (R > 200 or N * n_partners > 2048):
@@ -384,8 +420,6 @@ class EpiSelfAttention(nn.Module):
         autograd; the attention core is :class:`ops.EpiAttnFunction` (tcgen05 forward with log-sum-exp, cvd_epi_attn_bwd
         backward, the bias recomputed in registers both ways -- it has no gradient, epi_module.py:329,393).
         ``n`` bf16 [R,N,C] (LayerNorm output); returns (fp32 [R,N,C], None).  One partner per row."""
-        if H_mats is not None:
-            raise NotImplementedError("the H_mats (homography) branch (epi_module.py:301-310) is not built")
         if self.epi_fix_firstframe or self.epi_mono_direction:
             raise NotImplementedError("epi_fix_firstframe / epi_mono_direction are not built on the training path")
         proc = self.processor
@@ -397,9 +431,9 @@ class EpiSelfAttention(nn.Module):
         R, N, C = n.shape
         rowp = None
         if self.pos_encoder is not None and not self.epi_no_attention_mask:
-            if Fm is None:
-                raise NotImplementedError("F_mats=None (random pseudo lines on every row, epi_module.py:317-320) is not built")
-            rowp = self.pos_encoder.row_params(n, Fm)
+            # F_mats (RealEstate10K batches), H_mats (homography pseudo lines, train_epi_control.py:532-545) or neither
+            # (random pseudo lines): epi_module.py:301-320
+            rowp = self.pos_encoder.row_params(n, Fm, H_mats)
             if rowp.shape[0] != R:
                 raise NotImplementedError("the backward kernel takes one partner per row (2-view pairs, BASELINE config 5)")
         chunked = False

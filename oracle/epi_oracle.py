@@ -171,16 +171,51 @@ def effective_F(F_mats, theta=None):
     return Fe
 
 
-def epi_bias(F_mats, feat, S=256, pixel_band=3, decay_alpha=3, theta=None):
+def pseudo_line_matrices(slopes):
+    """get_pseudo_F_coords(random_slope=True) (epi_module.py:331-339) as matrices: the line through the query pixel with
+    direction angle ``slopes[r]`` is (cos, sin, -(cos x + sin y)) = M_r (x, y, 1)^T.  slopes [R] -> [R,3,3].
+    This is the WHOLE bias geometry of the F_mats=None branch (:317-320: random pseudo lines on every row)."""
+    c, s = torch.cos(slopes.float()), torch.sin(slopes.float())
+    M = torch.zeros(slopes.shape[0], 3, 3)
+    M[:, 0, 2], M[:, 1, 2], M[:, 2, 0], M[:, 2, 1] = c, s, -c, -s
+    return M
+
+
+def homography_line_matrices(H_mats, slopes, S=256):
+    """The H_mats branch (epi_module.py:301-310): every query pixel is warped by the row's homography (about the image
+    centre, perspective divide with +1e-6) and gets the pseudo line with angle ``slopes[r]`` through the WARPED point:
+        x'' = (x - c0, y - c0, 1), c0 = (S - 1) / 2;  (U, V, W) = H x'' (+1e-6 on W);  (u, v) = (U / W + c0, V / W + c0)
+        l_q = (cos, sin, -(cos u + sin v))
+    Lines are homogeneous and the distance |l . x_k| / |(a, b)| does not change under l -> W l, and
+        W l_q = (cos W, sin W, -(cos (U + c0 W) + sin (V + c0 W)))
+    is LINEAR in x'', hence in (x, y, 1): l_q ~ M_r x_q with
+        M_r = [cos h3'; sin h3'; -(cos h1 + sin h2 + (cos + sin) c0 h3')] T,   h3' = h3 + (0, 0, 1e-6),  T = shift by -c0.
+    (The reference divides by |(a,b)| + 1e-6 = 1 + 1e-6 where this form divides by |W| + 1e-6: a relative difference of
+    1e-6 (1 - 1/|W|), far below fp32 resolution for any usable homography.)  H_mats [R,3,3], slopes [R] -> [R,3,3]."""
+    H = H_mats.float()
+    c0 = (S - 1) / 2
+    c, s = torch.cos(slopes.float())[:, None], torch.sin(slopes.float())[:, None]
+    h1, h2 = H[:, 0], H[:, 1]
+    h3 = H[:, 2].clone()
+    h3[:, 2] += 1e-6
+    rows = torch.stack([c * h3, s * h3, -(c * h1 + s * h2 + (c + s) * c0 * h3)], dim=1)       # acts on x''
+    T = torch.tensor([[1.0, 0.0, -c0], [0.0, 1.0, -c0], [0.0, 0.0, 1.0]])
+    return rows @ T
+
+
+def epi_bias(F_mats, feat, S=256, pixel_band=3, decay_alpha=3, theta=None, first_frame=True):
     """Dense additive attention bias [R, N, N] fp32 (EpiEncoding.get_attn_map, F_mats branch,
     epi_module.py:311-329) followed by the NaN/inf scrub (epi_module.py:404-407).
 
       l_q   = F_r x_q ;  d[r,q,k] = |l_q . x_k| / (sqrt(a^2+b^2) + 1e-6)
       band  = pixel_band / (S // 2) * max_{q,k} d[r]
       bias  = -max(d - band, 0) * decay_alpha / (band + 1e-6)
+
+    ``first_frame=False``: the matrices already ARE the effective line matrices of every row (H_mats / F_mats=None
+    branches through ``homography_line_matrices`` / ``pseudo_line_matrices``): no first-frame override.
     """
     X = pixel_centres(feat, S)                                   # [N,3]
-    Fe = effective_F(F_mats, theta)                              # [R,3,3]
+    Fe = effective_F(F_mats, theta) if first_frame else F_mats.float()   # [R,3,3]
     L = torch.einsum("rij,nj->rni", Fe, X)                       # [R,N,3]  lines per query
     nrm = (L[..., 0] ** 2 + L[..., 1] ** 2).sqrt()[..., None]
     d = torch.einsum("rqi,ki->rqk", L, X).abs() / (nrm + 1e-6)   # [R,N,N]

@@ -220,6 +220,40 @@ def sampler():
     save("sampler", **out)
 
 
+def bias_pseudo():
+    """The two training-only branches of get_attn_map (epi_module.py:301-310 H_mats, :317-320 F_mats=None): the reference
+    draws one slope per row from the torch global RNG; the fixture stores the seed, the H matrices and the reference's
+    dense outputs (full at 8x8, sampled queries at 16x16)."""
+    out = {}
+    R = 32
+    rs = np.random.RandomState(909)
+    H = np.tile(np.eye(3), (R, 1, 1))
+    H[:, :2, :2] += 0.08 * rs.standard_normal((R, 2, 2))
+    H[:, :2, 2] += 12.0 * rs.standard_normal((R, 2))
+    H[:, 2, :2] += 4e-4 * rs.standard_normal((R, 2))
+    H = torch.from_numpy(H).float()
+    out["H"] = H
+    out["seed"] = 4321
+    for feat in (8, 16):
+        N = feat * feat
+        enc = EpiEncoding(320, max_feat_size=64, F_mat_size=256, rand_slope_on_first_frame=False)
+        for tag, kw in (("H", dict(H_mats=H)), ("none", dict())):
+            torch.manual_seed(4321)
+            b = enc.get_attn_map(torch.zeros(R, N, 1), **kw)
+            torch.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0, out=b)
+            k = f"f{feat}_{tag}_"
+            out[k + "sum"] = b.double().sum().item()
+            out[k + "min"] = b.min().item()
+            out[k + "q0"] = b[:, 0, :].clone()
+            out[k + "qmid"] = b[:, N // 2 + 3, :].clone()
+            out[k + "diag"] = torch.diagonal(b, dim1=1, dim2=2).clone()
+            if feat == 8:
+                out[k + "full"] = b.clone()
+    torch.manual_seed(4321)
+    out["slopes"] = torch.rand([R]) * math.pi
+    save("bias_pseudo", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -241,8 +275,8 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "plucker":
-        plucker()
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo"):
+        {"plucker": plucker, "bias_pseudo": bias_pseudo}[sys.argv[1]]()
         sys.exit(0)
     Fm = geometry()
     bias(Fm)
@@ -251,3 +285,4 @@ if __name__ == "__main__":
     temporal()
     sampler()
     plucker()
+    bias_pseudo()

@@ -114,3 +114,35 @@ def test_training_path_has_no_cpu_fallback_either():
                                        temporal_position_encoding_max_len=32, zero_initialize=False).train()
     with pytest.raises((NotImplementedError, cvd_b200.CvdError)):
         t(torch.zeros(2, 320, 16, 4, 4), cross_attention_kwargs={"pose_feature": None})
+
+
+def test_pseudo_line_branches_match_reference_fixture():
+    """The H_mats (epi_module.py:301-310) and F_mats=None (:317-320) branches of get_attn_map reduce to effective per-row
+    line matrices (cvd_b200.epi_module.homography_line_matrices / pseudo_line_matrices: plain torch, run here on the
+    CPU); the dense bias of those matrices (oracle.epi_bias, no first-frame override) must equal what the REFERENCE
+    computed for the same H matrices and the same slopes (tests/golden/bias_pseudo.npz, make_golden.py: bias_pseudo()),
+    and the product consumes the torch global RNG like the reference: one rand([rows]) per call."""
+    import math
+    import os
+    import numpy as np
+    import torch
+    from cvd_b200 import epi_module as em
+    from oracle import epi_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
+    H = torch.from_numpy(g["H"])
+    torch.manual_seed(int(g["seed"]))
+    slopes = torch.rand([H.shape[0]]) * math.pi                 # the draw row_params makes (and the reference made)
+    assert torch.equal(slopes, torch.from_numpy(g["slopes"]))
+    for feat in (8, 16):
+        for tag, M in (("H", em.homography_line_matrices(H, slopes, 256)), ("none", em.pseudo_line_matrices(slopes))):
+            b = O.epi_bias(M, feat, 256, first_frame=False)
+            k = f"f{feat}_{tag}_"
+            assert float((b[:, 0, :] - torch.from_numpy(g[k + "q0"])).abs().max()) < 5e-4
+            assert float((b[:, feat * feat // 2 + 3, :] - torch.from_numpy(g[k + "qmid"])).abs().max()) < 5e-4
+            assert float((torch.diagonal(b, dim1=1, dim2=2) - torch.from_numpy(g[k + "diag"])).abs().max()) < 5e-4
+            assert abs(float(b.double().sum()) / float(g[k + "sum"]) - 1) < 1e-6 and float(b.min()) == float(g[k + "min"])
+            if feat == 8:
+                assert float((b - torch.from_numpy(g[k + "full"])).abs().max()) < 5e-4
+    # the oracle's own restatement of the two branches is the same function
+    assert torch.allclose(em.homography_line_matrices(H, slopes, 256), O.homography_line_matrices(H, slopes, 256), atol=1e-6)
+    assert torch.equal(em.pseudo_line_matrices(slopes), O.pseudo_line_matrices(slopes))
