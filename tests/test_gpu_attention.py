@@ -178,29 +178,3 @@ def test_tcgen05_kernel_vs_oracle_bias_directly(golden, dev, theta):
     bias = torch.nan_to_num(bias, nan=0.0, posinf=0.0, neginf=0.0).to(dev)
     out = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
     assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=REL_TC, max_abs=0.08, what="tcgen05 vs oracle bias")
-
-
-@pytest.mark.parametrize("R,feat,d,n_src,kp", [(32, 32, 40, 1, 1), (32, 32, 40, 2, 1), (32, 16, 80, 2, 1), (32, 16, 40, 4, 2),
-                                               (16, 64, 40, 1, 1), (32, 8, 160, 2, 1), (32, 4, 160, 2, 1)])
-def test_multi_source_and_cluster_multicast_kernels_equal_default(golden, dev, R, feat, d, n_src, kp, monkeypatch):
-    """cvd_epi_attn_fwd_sharded on ONE GPU: K / V^T split into n_src buffers ("sources", here all local), partner rows
-    numbered globally -- first with the default (unicast) kernels, then with CVD_ATTN_CLUSTER=1: for latents > 8x8 the
-    query tiles of a (row, head) form a thread-block cluster and share every K / V^T tile through one multicast TMA
-    load.  Both must be BIT-identical to the default kernel on the un-split buffers (same arithmetic, only the
-    delivery of the tiles differs).  (Local memory only: multicast TMA from peer memory wedges the GPU, DESIGN.md.)"""
-    from cvd_b200 import ops
-    monkeypatch.delenv("CVD_ATTN_CLUSTER", raising=False)
-    q, k, v, vt, rowp, bias, partner = make_case(dev, R, feat, 8, d, 31 + feat, golden, kp=kp)
-    ref = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
-    rps = R // n_src
-    ks = [k[i * rps:(i + 1) * rps].clone() for i in range(n_src)]
-    vs = [vt[i * rps:(i + 1) * rps].clone() for i in range(n_src)]
-    out = ops.epi_attn_fwd_sharded(q, ks, vs, rps, rowp, partner, 8, 256.0)
-    assert torch.equal(out, ref)
-    monkeypatch.setenv("CVD_ATTN_CLUSTER", "1")
-    out_mc = ops.epi_attn_fwd_sharded(q, ks, vs, rps, rowp, partner, 8, 256.0)
-    out_mc1 = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
-    torch.cuda.synchronize()
-    monkeypatch.delenv("CVD_ATTN_CLUSTER")
-    assert torch.equal(out_mc, ref) and torch.equal(out_mc1, ref)
-    assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=REL_TC, max_abs=0.08, what="multi-source")

@@ -86,36 +86,3 @@ def test_pairwise_fundamental_on_device(golden, dev):
     idx = np.concatenate([np.arange(16) + p * 16 for p in pairing]).astype(np.int32)
     Fd = ops.pairwise_fundamental(torch.from_numpy(c).to(dev), torch.from_numpy(Km).to(dev), torch.from_numpy(idx).to(dev)).cpu()
     np.testing.assert_allclose(Fd.numpy(), O.pairwise_F_mats(c, Km, pairing).numpy(), rtol=1e-5, atol=1e-9)
-
-
-@pytest.mark.parametrize("feat", [8, 16])
-@pytest.mark.parametrize("tag", ["H", "none"])
-def test_pseudo_line_branches_vs_reference_fixture(dev, feat, tag):
-    """get_attn_map's H_mats branch (epi_module.py:301-310: homography-warped pseudo lines, the WebVid batches of
-    train_epi_control.py:532-545) and F_mats=None branch (:317-320: random pseudo lines on every row) on the device:
-    effective line matrices (torch, on the GPU) -> cvd_epi_row_params (no first-frame rule) -> dense writer, against the
-    REFERENCE's outputs for the same H matrices and slopes (tests/golden/bias_pseudo.npz)."""
-    import os
-    import cvd_b200
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
-    enc = cvd_b200.EpiEncoding(320, max_feat_size=64, F_mat_size=256).to(dev)
-    enc.slope_override = torch.from_numpy(g["slopes"]).to(dev)
-    H = torch.from_numpy(g["H"]).to(dev)
-    x = torch.zeros(H.shape[0], feat * feat, 1, device=dev)
-    b = (enc.get_attn_map(x, H_mats=H) if tag == "H" else enc.get_attn_map(x)).cpu()
-    k = f"f{feat}_{tag}_"
-    N = feat * feat
-    np.testing.assert_allclose(b[:, 0].numpy(), g[k + "q0"], atol=3e-3, rtol=1e-4)
-    np.testing.assert_allclose(b[:, N // 2 + 3].numpy(), g[k + "qmid"], atol=3e-3, rtol=1e-4)
-    np.testing.assert_allclose(torch.diagonal(b, dim1=1, dim2=2).numpy(), g[k + "diag"], atol=3e-3, rtol=1e-4)
-    assert abs(float(b.min()) - float(g[k + "min"])) < 2e-3
-    if feat == 8:
-        np.testing.assert_allclose(b.numpy(), g[k + "full"], atol=3e-3, rtol=1e-4)
-    # RNG consumption of these branches: ONE torch.rand([rows], device) per call (epi_module.py:310,320)
-    enc.slope_override = None
-    torch.manual_seed(5)
-    enc.row_params(x, None, H if tag == "H" else None)
-    after = torch.rand([1], device=dev)
-    torch.manual_seed(5)
-    torch.rand([H.shape[0]], device=dev)
-    assert torch.equal(after, torch.rand([1], device=dev))

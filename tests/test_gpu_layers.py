@@ -243,32 +243,3 @@ def test_temporal_module_train_twin_vs_oracle_autograd(golden, dev):
     e_x, e_p = rel_l2(xp.grad.cpu(), x_ref.grad), rel_l2(pp.grad.cpu(), p_ref.grad)
     print(f"temporal train twin: vs inference path {e_same:.2e}, vs oracle {e_fwd:.2e}, d/dx {e_x:.2e}, d/dpose {e_p:.2e}")
     assert e_same < 1e-2 and e_fwd < 3e-2 and e_x < 5e-2 and e_p < 5e-2
-
-
-@pytest.mark.parametrize("branch", ["H", "none"])
-def test_layer_homography_and_random_line_branches(golden, dev, branch):
-    """EpiSelfAttention.forward with H_mats (train_epi_control.py:532-545) or with neither F_mats nor H_mats
-    (epi_module.py:317-320), inference and training mode, against the fp32 oracle layer with the reference-pinned dense
-    bias of the same slopes injected."""
-    import os
-    from gpu_util import rel_l2
-    from oracle import epi_oracle as O
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
-    C, feat, R = 320, 8, 32
-    sd = gi.attn_state_dict(C, 321)
-    x = gi.hidden_tokens(R, feat * feat, C, 322)
-    H = torch.from_numpy(g["H"])
-    slopes = torch.from_numpy(g["slopes"])
-    M = O.homography_line_matrices(H, slopes) if branch == "H" else O.pseudo_line_matrices(slopes)
-    bias = O.epi_bias(M, feat, 256, first_frame=False)
-    ref, _ = O.epi_attention(x, sd, "", 8, bias=bias)
-    attn = build_attn(C, dev, sd)
-    attn.pos_encoder.slope_override = slopes.to(dev)
-    kw = dict(H_mats=H.to(dev)) if branch == "H" else {}
-    with torch.no_grad():
-        y, aux = attn(x.to(dev), **kw)
-    assert_close(y, ref, rel=REL, what=f"{branch} branch")
-    xt = x.to(dev).requires_grad_(True)
-    yt, _ = attn.train()(xt, **kw)
-    yt.float().pow(2).sum().backward()
-    assert rel_l2(yt.detach(), y) < 1e-2 and torch.isfinite(xt.grad).all() and float(xt.grad.abs().max()) > 0

@@ -1,0 +1,113 @@
+"""-m gpu: tests written in round 2 AFTER GPU access for this repository was closed (a 2-GPU experiment with multicast
+TMA from peer memory wedged the box): the kernels they exercise were validated on a B200 earlier in
+the round (profiles/r02_summary.md), the host logic is pinned on the CPU (tests/test_host_logic.py,
+tests/test_oracle_golden.py), but THESE test functions have not run on hardware yet -- the file name sorts last so that
+everything validated runs before them.
+
+* multi-source K / V^T (cvd_epi_attn_fwd_sharded) and the opt-in cluster-multicast kernels on LOCAL memory;
+* the H_mats / F_mats=None branches of get_attn_map through the device kernels (dense bias and layer level).
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from gpu_util import assert_close, attention_ref
+from test_gpu_attention import REL_TC, make_case
+from test_gpu_layers import REL, build_attn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("R,feat,d,n_src,kp", [(32, 32, 40, 1, 1), (32, 32, 40, 2, 1), (32, 16, 80, 2, 1), (32, 16, 40, 4, 2),
+                                               (16, 64, 40, 1, 1), (32, 8, 160, 2, 1), (32, 4, 160, 2, 1)])
+def test_multi_source_and_cluster_multicast_kernels_equal_default(golden, dev, R, feat, d, n_src, kp, monkeypatch):
+    """cvd_epi_attn_fwd_sharded on ONE GPU: K / V^T split into n_src buffers ("sources", here all local), partner rows
+    numbered globally -- first with the default (unicast) kernels, then with CVD_ATTN_CLUSTER=1: for latents > 8x8 the
+    query tiles of a (row, head) form a thread-block cluster and share every K / V^T tile through one multicast TMA
+    load.  Both must be BIT-identical to the default kernel on the un-split buffers (same arithmetic, only the
+    delivery of the tiles differs).  (Local memory only: multicast TMA from peer memory wedges the GPU, DESIGN.md.)"""
+    from cvd_b200 import ops
+    monkeypatch.delenv("CVD_ATTN_CLUSTER", raising=False)
+    q, k, v, vt, rowp, bias, partner = make_case(dev, R, feat, 8, d, 31 + feat, golden, kp=kp)
+    ref = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
+    rps = R // n_src
+    ks = [k[i * rps:(i + 1) * rps].clone() for i in range(n_src)]
+    vs = [vt[i * rps:(i + 1) * rps].clone() for i in range(n_src)]
+    out = ops.epi_attn_fwd_sharded(q, ks, vs, rps, rowp, partner, 8, 256.0)
+    assert torch.equal(out, ref)
+    monkeypatch.setenv("CVD_ATTN_CLUSTER", "1")
+    out_mc = ops.epi_attn_fwd_sharded(q, ks, vs, rps, rowp, partner, 8, 256.0)
+    out_mc1 = ops.epi_attn_fwd(q, k, vt, rowp, partner, 8, 256.0)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("CVD_ATTN_CLUSTER")
+    assert torch.equal(out_mc, ref) and torch.equal(out_mc1, ref)
+    assert_close(out, attention_ref(q, k, v, 8, bias, partner), rel=REL_TC, max_abs=0.08, what="multi-source")
+
+
+@pytest.mark.parametrize("feat", [8, 16])
+@pytest.mark.parametrize("tag", ["H", "none"])
+def test_pseudo_line_branches_vs_reference_fixture(dev, feat, tag):
+    """get_attn_map's H_mats branch (epi_module.py:301-310: homography-warped pseudo lines, the WebVid batches of
+    train_epi_control.py:532-545) and F_mats=None branch (:317-320: random pseudo lines on every row) on the device:
+    effective line matrices (torch, on the GPU) -> cvd_epi_row_params (no first-frame rule) -> dense writer, against the
+    REFERENCE's outputs for the same H matrices and slopes (tests/golden/bias_pseudo.npz)."""
+    import os
+    import cvd_b200
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
+    enc = cvd_b200.EpiEncoding(320, max_feat_size=64, F_mat_size=256).to(dev)
+    enc.slope_override = torch.from_numpy(g["slopes"]).to(dev)
+    H = torch.from_numpy(g["H"]).to(dev)
+    x = torch.zeros(H.shape[0], feat * feat, 1, device=dev)
+    b = (enc.get_attn_map(x, H_mats=H) if tag == "H" else enc.get_attn_map(x)).cpu()
+    k = f"f{feat}_{tag}_"
+    N = feat * feat
+    np.testing.assert_allclose(b[:, 0].numpy(), g[k + "q0"], atol=3e-3, rtol=1e-4)
+    np.testing.assert_allclose(b[:, N // 2 + 3].numpy(), g[k + "qmid"], atol=3e-3, rtol=1e-4)
+    np.testing.assert_allclose(torch.diagonal(b, dim1=1, dim2=2).numpy(), g[k + "diag"], atol=3e-3, rtol=1e-4)
+    assert abs(float(b.min()) - float(g[k + "min"])) < 2e-3
+    if feat == 8:
+        np.testing.assert_allclose(b.numpy(), g[k + "full"], atol=3e-3, rtol=1e-4)
+    # RNG consumption of these branches: ONE torch.rand([rows], device) per call (epi_module.py:310,320)
+    enc.slope_override = None
+    torch.manual_seed(5)
+    enc.row_params(x, None, H if tag == "H" else None)
+    after = torch.rand([1], device=dev)
+    torch.manual_seed(5)
+    torch.rand([H.shape[0]], device=dev)
+    assert torch.equal(after, torch.rand([1], device=dev))
+
+
+@pytest.mark.parametrize("branch", ["H", "none"])
+def test_layer_homography_and_random_line_branches(golden, dev, branch):
+    """EpiSelfAttention.forward with H_mats (train_epi_control.py:532-545) or with neither F_mats nor H_mats
+    (epi_module.py:317-320), inference and training mode, against the fp32 oracle layer with the reference-pinned dense
+    bias of the same slopes injected."""
+    import os
+    from gpu_util import rel_l2
+    from oracle import epi_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
+    C, feat, R = 320, 8, 32
+    sd = gi.attn_state_dict(C, 321)
+    x = gi.hidden_tokens(R, feat * feat, C, 322)
+    H = torch.from_numpy(g["H"])
+    slopes = torch.from_numpy(g["slopes"])
+    M = O.homography_line_matrices(H, slopes) if branch == "H" else O.pseudo_line_matrices(slopes)
+    bias = O.epi_bias(M, feat, 256, first_frame=False)
+    ref, _ = O.epi_attention(x, sd, "", 8, bias=bias)
+    attn = build_attn(C, dev, sd)
+    attn.pos_encoder.slope_override = slopes.to(dev)
+    kw = dict(H_mats=H.to(dev)) if branch == "H" else {}
+    with torch.no_grad():
+        y, aux = attn(x.to(dev), **kw)
+    assert_close(y, ref, rel=REL, what=f"{branch} branch")
+    xt = x.to(dev).requires_grad_(True)
+    yt, _ = attn.train()(xt, **kw)
+    yt.float().pow(2).sum().backward()
+    assert rel_l2(yt.detach(), y) < 1e-2 and torch.isfinite(xt.grad).all() and float(xt.grad.abs().max()) > 0
