@@ -19,4 +19,6 @@ from .motion_module import (AttnProcessor, PoseAdaptorAttnProcessor, PositionalE
                             TemporalTransformer3DModel, TemporalTransformerBlock, VanillaTemporalModule,
                             get_motion_module)
 
-__version__ = "0.1.0"
+from .pose_encoder import CameraPoseEncoder  # noqa: F401
+
+__version__ = "0.2.0"

@@ -182,6 +182,23 @@ class TemporalTransformerBlock(nn.Module):
         hb = ops.residual_add_(hs, y, self.ff._w.f32("b2", self.ff.net[2].bias), 1.0, want_bf16=want_bf16)
         return hs, hb
 
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None,
+                cross_attention_kwargs: Dict[str, Any] = {}):
+        """motion_module.py:447-460 on tokens [T, F, C] (how the CameraCtrl pose encoder calls the block,
+        pose_adaptor.py:322-324): CUDA kernels at inference, the autograd twin when a graph is wanted."""
+        if attention_mask is not None:
+            raise _lib.CvdError("temporal attention masks are not supported (the reference passes None)")
+        pose = cross_attention_kwargs.get("pose_feature", None)
+        scale = cross_attention_kwargs.get("scale", None)
+        if _wants_grad(self, hidden_states, pose):
+            if not hidden_states.is_cuda:
+                raise _lib.CvdError("cvd_b200 has no CPU path: hidden_states must be a CUDA tensor")
+            return self.forward_train(hidden_states.float(), pose, scale).to(hidden_states.dtype)
+        if pose is not None:
+            raise _lib.CvdError("token-level calls take the pose feature in video layout through VanillaTemporalModule")
+        hs, _ = self.forward_stream(hidden_states.float().contiguous().clone())
+        return hs.to(hidden_states.dtype)
+
     def forward_train(self, hs, pose_tokens=None, scale=None):
         """Autograd twin of :meth:`forward_stream` (motion_module.py:447-460): fp32 stream [T, F, C] in, out."""
         bf = torch.bfloat16

@@ -65,6 +65,38 @@ class _Linear(nn.Linear):
         return F.linear(hidden_states, self.weight, self.bias)
 
 
+class AttnProcessor2_0:
+    """diffusers.models.attention_processor.AttnProcessor2_0 (0.24.0), the default processor of ``Attention`` -- what the
+    TemporalSelfAttention blocks of the CameraCtrl pose encoder run (models/pose_adaptor.py:290-300 never installs
+    another one): to_q / to_k / to_v, heads split, ``F.scaled_dot_product_attention`` with 1/sqrt(d) scaling, to_out
+    (Linear + Dropout), optional residual, division by ``rescale_output_factor``.  Restated from the published source
+    (3-D inputs, no group / spatial norm: the only configuration on this path)."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None, scale=1.0):
+        residual = hidden_states
+        batch_size = hidden_states.shape[0]
+        if attention_mask is not None:
+            seq = (hidden_states if encoder_hidden_states is None else encoder_hidden_states).shape[1]
+            attention_mask = attn.prepare_attention_mask(attention_mask, seq, batch_size)
+            attention_mask = attention_mask.view(batch_size, attn.heads, -1, attention_mask.shape[-1])
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        head_dim = key.shape[-1] // attn.heads
+        query = query.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        key = key.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        value = value.view(batch_size, -1, attn.heads, head_dim).transpose(1, 2)
+        hidden_states = F.scaled_dot_product_attention(query, key, value, attn_mask=attention_mask, dropout_p=0.0,
+                                                       is_causal=False)
+        hidden_states = hidden_states.transpose(1, 2).reshape(batch_size, -1, attn.heads * head_dim).to(query.dtype)
+        hidden_states = attn.to_out[1](attn.to_out[0](hidden_states))
+        if attn.residual_connection:
+            hidden_states = hidden_states + residual
+        return hidden_states / attn.rescale_output_factor
+
+
 class Attention(nn.Module):
     """diffusers.models.attention_processor.Attention (0.24.0), the subset used.
 
@@ -92,7 +124,8 @@ class Attention(nn.Module):
         self.to_k = _Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
         self.to_v = _Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
         self.to_out = nn.ModuleList([_Linear(self.inner_dim, query_dim, bias=out_bias), nn.Dropout(dropout)])
-        self.processor = processor
+        # diffusers: ``AttnProcessor2_0() if hasattr(F, "scaled_dot_product_attention") and self.scale_qk else AttnProcessor()``
+        self.processor = processor if processor is not None else AttnProcessor2_0()
 
     def set_processor(self, processor):
         # diffusers pops a previously registered nn.Module processor before re-assigning

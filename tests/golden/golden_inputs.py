@@ -140,3 +140,41 @@ TEMPORAL_CASES = [
     dict(name="tmp_pose", C=320, feat=4, B=2, seed=2100, pose=True),
     dict(name="tmp_nopose", C=320, feat=4, B=2, seed=2200, pose=False),
 ]
+
+
+# ---- CameraCtrl pose encoder (pose_adaptor.py:248-329): two small configurations that take every structural branch -----
+POSE_ENCODER_CASES = [
+    # the shipped configuration's structure (configs/inference_config.yaml:34-46) at reduced width
+    dict(name="pe_cfg", kwargs=dict(downscale_factor=8, channels=[64, 128, 128], nums_rb=2, cin=384, ksize=1, sk=True,
+                                    use_conv=False, compression_factor=1, temporal_attention_nhead=8,
+                                    attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                                    temporal_position_encoding_max_len=16), B=2, H=32, W=32, seed=7100),
+    # 3x3 convolutions, strided-convolution downsampling, three ResNet blocks per level, no positional encoding
+    dict(name="pe_conv", kwargs=dict(downscale_factor=4, channels=[32, 64], nums_rb=3, cin=96, ksize=3, sk=True,
+                                     use_conv=True, compression_factor=1, temporal_attention_nhead=4,
+                                     attention_block_types=["Temporal_Self"], temporal_position_encoding=False,
+                                     temporal_position_encoding_max_len=16), B=1, H=16, W=24, seed=7200),
+]
+
+
+def fill_state_dict(shapes, seed):
+    """Deterministic weights for a {name: shape} table (sorted by name, one numpy stream per tensor): matrices and
+    convolutions ~ N(0, 0.5^2 / fan_in), 1-D ``weight`` (norm scales) ~ 1 + 0.1 N(0,1), biases ~ 0.1 N(0,1)."""
+    sd = {}
+    for i, name in enumerate(sorted(shapes)):
+        shape = tuple(shapes[name])
+        rs = np.random.RandomState(seed + i)
+        if len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            w = rs.standard_normal(shape) * (0.5 / np.sqrt(fan_in))
+        elif name.endswith("weight"):
+            w = 1.0 + 0.1 * rs.standard_normal(shape)
+        else:
+            w = 0.1 * rs.standard_normal(shape)
+        sd[name] = torch.from_numpy(w.astype(np.float32))
+    return sd
+
+
+def plucker_like(B, H, W, seed, frames=16):
+    rs = np.random.RandomState(seed)
+    return torch.from_numpy(rs.standard_normal((B, 6, frames, H, W)).astype(np.float32))

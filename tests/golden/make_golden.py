@@ -254,6 +254,28 @@ def bias_pseudo():
     save("bias_pseudo", **out)
 
 
+def pose_encoder():
+    """CameraPoseEncoder of the reference (models/pose_adaptor.py:248-329) on two small configurations; the fixture holds
+    the parameter table (names + shapes: the state_dict contract) and the feature maps."""
+    from animatediff.models.pose_adaptor import CameraPoseEncoder
+    out = {}
+    for case in gi.POSE_ENCODER_CASES:
+        m = CameraPoseEncoder(**case["kwargs"]).eval()
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("pos_encoder.pe")}
+        sd = gi.fill_state_dict(shapes, case["seed"])
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.endswith("pos_encoder.pe") for k in missing), (missing, unexpected)
+        x = gi.plucker_like(case["B"], case["H"], case["W"], case["seed"] + 1)
+        feats = m(x)
+        n = case["name"]
+        out[n + "_names"] = np.array(sorted(shapes))
+        out[n + "_shapes"] = np.array([str(shapes[k]) for k in sorted(shapes)])
+        out[n + "_n"] = len(feats)
+        for i, f in enumerate(feats):
+            out[f"{n}_feat{i}"] = f
+    save("pose_encoder", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -275,8 +297,8 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo"):
-        {"plucker": plucker, "bias_pseudo": bias_pseudo}[sys.argv[1]]()
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder"):
+        {"plucker": plucker, "bias_pseudo": bias_pseudo, "pose_encoder": pose_encoder}[sys.argv[1]]()
         sys.exit(0)
     Fm = geometry()
     bias(Fm)
@@ -286,3 +308,4 @@ if __name__ == "__main__":
     sampler()
     plucker()
     bias_pseudo()
+    pose_encoder()

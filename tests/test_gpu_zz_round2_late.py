@@ -111,3 +111,24 @@ def test_layer_homography_and_random_line_branches(golden, dev, branch):
     yt, _ = attn.train()(xt, **kw)
     yt.float().pow(2).sum().backward()
     assert rel_l2(yt.detach(), y) < 1e-2 and torch.isfinite(xt.grad).all() and float(xt.grad.abs().max()) > 0
+
+
+@pytest.mark.parametrize("case", gi.POSE_ENCODER_CASES, ids=lambda c: c["name"])
+def test_pose_encoder_inference_path_vs_reference_fixture(dev, case):
+    """cvd_b200.CameraPoseEncoder.forward on the device (cuDNN convolutions + this package's temporal transformer
+    block kernels) against the reference's CameraPoseEncoder (tests/golden/pose_encoder.npz); the torch twin of the same
+    module is pinned to the same fixture on the CPU (tests/test_host_logic.py)."""
+    import os
+    import cvd_b200
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pose_encoder.npz"))
+    n = case["name"]
+    m = cvd_b200.CameraPoseEncoder(**case["kwargs"]).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("pos_encoder.pe")}
+    m.load_state_dict(gi.fill_state_dict(shapes, case["seed"]), strict=False)
+    m = m.to(dev)
+    x = gi.plucker_like(case["B"], case["H"], case["W"], case["seed"] + 1).to(dev)
+    with torch.no_grad():
+        feats = m(x)
+    assert len(feats) == int(g[n + "_n"])
+    for i, f in enumerate(feats):
+        assert_close(f, torch.from_numpy(g[f"{n}_feat{i}"]), rel=REL, what=f"{n} level {i}")

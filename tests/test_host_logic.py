@@ -146,3 +146,37 @@ def test_pseudo_line_branches_match_reference_fixture():
     # the oracle's own restatement of the two branches is the same function
     assert torch.allclose(em.homography_line_matrices(H, slopes, 256), O.homography_line_matrices(H, slopes, 256), atol=1e-6)
     assert torch.equal(em.pseudo_line_matrices(slopes), O.pseudo_line_matrices(slopes))
+
+
+def test_pose_encoder_matches_reference_fixture():
+    """cvd_b200.CameraPoseEncoder against the REFERENCE's CameraPoseEncoder (models/pose_adaptor.py:248-329, fixture
+    tests/golden/pose_encoder.npz from make_golden.py: pose_encoder()): identical parameter names and shapes (the
+    state_dict contract: a CameraCtrl checkpoint loads unchanged), and the feature maps of the autograd twin (plain
+    torch ops, run here on the CPU by calling ``forward_train`` directly; bf16 GEMM operands -> rel-L2 2e-2).  The
+    public ``forward`` refuses CPU tensors like the rest of the package."""
+    import os
+    import numpy as np
+    import pytest
+    import torch
+    import cvd_b200
+    import golden_inputs as gi
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pose_encoder.npz"))
+    for case in gi.POSE_ENCODER_CASES:
+        n = case["name"]
+        m = cvd_b200.CameraPoseEncoder(**case["kwargs"]).eval()
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith("pos_encoder.pe")}
+        assert sorted(mine) == g[n + "_names"].tolist()
+        assert [str(mine[k]) for k in sorted(mine)] == g[n + "_shapes"].tolist()
+        missing, unexpected = m.load_state_dict(gi.fill_state_dict(mine, case["seed"]), strict=False)
+        assert not unexpected and all(k.endswith("pos_encoder.pe") for k in missing)
+        x = gi.plucker_like(case["B"], case["H"], case["W"], case["seed"] + 1)
+        with pytest.raises(cvd_b200.CvdError):
+            m(x)
+        with torch.no_grad():
+            feats = m.forward_train(x)
+        assert len(feats) == int(g[n + "_n"])
+        for i, f in enumerate(feats):
+            ref = torch.from_numpy(g[f"{n}_feat{i}"])
+            assert f.shape == ref.shape
+            err = float((f.double() - ref.double()).norm() / ref.double().norm())
+            assert err < 2e-2, (n, i, err)
