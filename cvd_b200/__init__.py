@@ -10,7 +10,7 @@ Public surface = the reference's own plugin interface for this path
 All compute runs in ``cvd_b200/lib/libcvd_b200.so`` (C ABI: ``include/cvd_b200.h``); importing
 the package does not load it, the first op does -- and raises if it has not been built.
 """
-from . import _lib, geometry, ops  # noqa: F401
+from . import _lib, geometry, ops, training  # noqa: F401
 from ._lib import CvdError  # noqa: F401
 from .graphs import GraphedModule  # noqa: F401
 from .epi_module import (EpiAttnProcessor, EpiEncoding, EpiModule, EpiSelfAttention, EpiTransformer3DModel,  # noqa: F401

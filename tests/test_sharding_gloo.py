@@ -62,3 +62,46 @@ def test_view_shard_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cvd_b200 import training
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.Linear(40, 8))
+        net[1].requires_grad_(False)
+        for p in net[2].parameters():              # a frozen layer in the middle, and one parameter without a gradient
+            p.requires_grad_(False)
+        params = training.trainable_epi_parameters(net)
+        assert len(params) == 4
+        g = torch.Generator().manual_seed(100 + rank)           # every rank its own batch (train_epi_control.py:283-290)
+        x = torch.randn(16, 24, generator=g)
+        net(x).pow(2).mean().backward()
+        local = [p.grad.clone() for p in params]
+        n_b = training.allreduce_gradients(params, comm_dtype=torch.float32, bucket_bytes=4096)
+        assert n_b >= 2                                          # several buckets at this bucket size
+        ret[rank] = ([t.numpy() for t in local], [p.grad.numpy().copy() for p in params])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_equals_mean_of_rank_gradients():
+    """cvd_b200.training.allreduce_gradients over gloo (fp32 wire format: exact): every rank ends with the mean of the
+    ranks' local gradients, bucketed in reverse parameter order, frozen parameters untouched."""
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, port, ret), nprocs=2, join=True)
+    (l0, r0), (l1, r1) = ret[0], ret[1]
+    for a, b, m0, m1 in zip(l0, l1, r0, r1):
+        mean = (a + b) / 2
+        assert np.allclose(m0, mean, atol=1e-7) and np.allclose(m1, mean, atol=1e-7)
+    from cvd_b200 import training
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (10, 300, 20, 500)]
+    for p in ps:
+        p.grad = torch.zeros_like(p)
+    sizes = [[p.numel() for p in b] for b in training.gradient_buckets(ps, 1200, 2)]
+    assert sizes == [[500, 20], [300, 10]]                       # reverse parameter order, greedy 600-element buckets
