@@ -394,7 +394,9 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    # CVD_BENCH_DRYRUN_DEVICE exists for tests/test_bench_dryrun.py only: the CPU build box runs this function's control flow
+    # with the kernels and the CUDA runtime replaced by test doubles.  The real ops refuse anything but CUDA tensors.
+    dev = torch.device(os.environ.get("CVD_BENCH_DRYRUN_DEVICE", "cuda"), local)
     shard = peer = None
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: if the caller asks for NCCL logging (NCCL_DEBUG=INFO, e.g. to count

@@ -23,7 +23,7 @@ def reference_gpu_layer(x, sd, heads, F_mats, S=256, autocast=False):
     mask = bias.repeat_interleave(heads, dim=0).view(R, heads, N, N)      # x8 copy, as prepare_attention_mask does
     idx = torch.cat([torch.arange(R // 2, R), torch.arange(0, R // 2)]).to(x.device)
     d = C // heads
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+    with torch.autocast(x.device.type, dtype=torch.bfloat16, enabled=autocast):
         enc = x[idx]
         q = F.linear(x, sd["to_q.weight"]).view(R, N, heads, d).transpose(1, 2)
         k = F.linear(enc, sd["to_k.weight"]).view(R, N, heads, d).transpose(1, 2)

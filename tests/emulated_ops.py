@@ -190,8 +190,14 @@ def install(monkeypatch):
     GEMM): on the CPU it is emulated as an fp32 product of the bf16-rounded operands."""
     from cvd_b200 import ops
     g = globals()
+
+    def counted(fn):
+        def call(*a, **k):
+            ops.LAUNCHES += 1                      # the real wrappers count their launches (bench.py: gpu_launches)
+            return fn(*a, **k)
+        return call
     for name in EMULATED:
-        monkeypatch.setattr(ops, name, g[name])
+        monkeypatch.setattr(ops, name, counted(g[name]))
     real_mm = torch.mm
 
     def mm(a, b, *, out_dtype=None, out=None):

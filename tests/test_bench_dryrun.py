@@ -1,0 +1,196 @@
+"""CPU dry run of ``bench.py``'s N = 1 control flow (the driver-facing artifact: one JSON line per run), with the kernels
+replaced by the plain-torch test double (tests/emulated_ops.py), the CUDA runtime calls (streams, events, graphs, pinned
+memory) by no-op stand-ins, and the workload shrunk to two small shapes.  It cannot say anything about speed; it checks
+that every code path of the default run executes and that the line carries every key the contract names -- the parts of
+``bench.py`` that changed in round 2 after GPU access was closed (value loop refactor, per-shape roofline, glue roofline,
+reference-GPU leg) would otherwise run for the first time in the driver's hands."""
+import contextlib
+import io
+import json
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+import emulated_ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def wait_stream(self, s):
+        pass
+
+    def wait_event(self, e):
+        pass
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def wait(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+class _Graph:
+    def replay(self):
+        pass
+
+
+@contextlib.contextmanager
+def _graph_ctx(graph, stream=None):
+    yield
+
+
+def fake_cuda(monkeypatch):
+    cur = _Stream()
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: cur)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", _Event)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(torch.cuda, "graph", _graph_ctx)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None)
+
+
+def test_bench_default_run_control_flow(monkeypatch):
+    fake_cuda(monkeypatch)
+    emulated_ops.install(monkeypatch)
+    from cvd_b200 import _lib, ops
+    monkeypatch.setattr(_lib, "load", lambda: None)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setenv("CVD_BENCH_DRYRUN_DEVICE", "cpu")
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "SHAPES", [(8, 320), (4, 320)])
+    monkeypatch.setattr(bench, "CALLS_PER_SHAPE", 2)
+    # the glue measurement at its real shapes is minutes of CPU time: keep its code path, shrink its shapes
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import profile_glue
+    real_measure = profile_glue.measure
+    monkeypatch.setattr(profile_glue, "measure", lambda dev, peak: real_measure(dev, peak, shapes=((4, 64),), iters=2))
+    monkeypatch.setattr(bench, "cpu_reference_step", lambda R, reps, warm: ([1.0] * reps, 1e9, 1))
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="ours", no_denoise=True, no_extras=False, exchange="dma",
+                                 no_graph=False)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        bench.run_ours(args)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline",
+                "roofline_by_shape", "roofline_glue", "reference_gpu"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["dtype"] == "bf16"
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+    assert isinstance(d["roofline_by_shape"], list) and len(d["roofline_by_shape"]) == 2, d["roofline_by_shape"]
+    assert isinstance(d["roofline_glue"], list) and len(d["roofline_glue"]) >= 10, d["roofline_glue"]
+    assert "error" not in d["reference_gpu"], d["reference_gpu"]
+    assert len(d["reference_gpu"]["per_shape"]) == 2 and all(r["rel_l2_vs_fp32"] < 3e-2 for r in d["reference_gpu"]["per_shape"])
+    # 2 shapes x 2 calls x (prepass + attention) per step
+    assert d["gpu_launches"] == 2 * 2 * 2 * 2
+
+
+def test_bench_reference_arm_honours_warmup(monkeypatch, capsys):
+    sys.path.insert(0, ROOT)
+    import bench
+    seen = {}
+
+    def fake(R, reps, warm):
+        seen["warm"], seen["reps"] = warm, reps
+        return [0.5] * reps, 1e9, 3
+    monkeypatch.setattr(bench, "cpu_reference_step", fake)
+    bench.run_reference(types.SimpleNamespace(gpus=1, steps=4, warmup=2))
+    d = json.loads(capsys.readouterr().out.strip())
+    assert seen == {"warm": 2, "reps": 4} and d["impl"] == "reference" and d["warmup"] == 2 and d["steps"] == 4
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_sharded_run_control_flow(monkeypatch):
+    """The N > 1 branch of ``run_ours`` in ONE process: rank 0 of a pretended world of 2 whose "peer" buffers alias its own
+    (symmetric memory, the process group and the collectives replaced by stand-ins).  Exercises the chunk / run plans of
+    the copy-engine exchange, the in-kernel branch of the small latents, the graph-capture path with its launch
+    accounting, the eager passes that time the dominant kernel, the sharded e2e layers and the JSON line."""
+    import numpy as np
+    import torch.distributed as dist
+    fake_cuda(monkeypatch)
+    emulated_ops.install(monkeypatch)
+    from cvd_b200 import _lib, ops, sharding
+    monkeypatch.setattr(_lib, "load", lambda: None)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setenv("CVD_BENCH_DRYRUN_DEVICE", "cpu")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("LOCAL_RANK", "0")
+    monkeypatch.setattr(dist, "init_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "destroy_process_group", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "get_world_size", lambda group=None: 2)
+    monkeypatch.setattr(dist, "get_rank", lambda group=None: 0)
+    monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+    monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: None)
+    barriers = []
+
+    class Handle:
+        def __init__(self, t):
+            self.t = t
+
+        def get_buffer(self, rank, shape, dtype):
+            return self.t                                   # the "peer's" copy aliases the local one
+
+        def barrier(self, channel=0, timeout_ms=0):
+            barriers.append(timeout_ms)
+
+    class FakePeer:
+        mode = "hidden"
+
+        def __init__(self, shard):
+            self.shard = shard
+
+        def alloc(self, shape, dtype, device):
+            t = torch.empty(*shape, dtype=dtype, device=device)
+            return t, [0, 0], Handle(t)
+
+        def identity_index(self, n, device):
+            return torch.arange(n, device=device, dtype=torch.int32)
+
+        def exchange(self, x, partner):
+            return x[(partner.long() % x.shape[0])]
+
+    monkeypatch.setattr(sharding, "PeerExchange", FakePeer)
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "SHAPES", [(32, 16), (16, 16), (8, 64), (4, 64)])      # all four exchange branches, tiny C
+    monkeypatch.setattr(bench, "HEADS", 2)
+    monkeypatch.setattr(bench, "CALLS_PER_SHAPE", 1)
+    monkeypatch.setattr(bench, "cpu_reference_step", lambda R, reps, warm: ([1.0] * reps, 1e9, 1))
+    args = types.SimpleNamespace(gpus=2, steps=2, warmup=1, impl="ours", no_denoise=True, no_extras=False, exchange="dma",
+                                 no_graph=False)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        bench.run_ours(args)
+    d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][0])
+    assert d["n_gpus"] == 2 and d["config"]["views_total"] == 4 and "copy engines" in d["config"]["parallelism"]
+    assert all(t_ == sharding.BARRIER_TIMEOUT_MS for t_ in barriers) and len(barriers) > 0
+    # per step: 4 prepasses + 3 chunk launches (32x32) + 3 (16x16) + 1 + 1 in-kernel launches
+    assert d["gpu_launches"] == 2 * (4 + 3 + 3 + 1 + 1), d["gpu_launches"]
+    assert d["roofline"]["ms_per_launch"] == 3.0            # three chunk launches of 1.0 "ms" each add up to one call
+    assert "roofline_by_shape" not in d and "reference_gpu" not in d      # N = 1 extras only
