@@ -45,6 +45,7 @@ CALLS_PER_SHAPE = 10                                     # 5 epi modules x 2 att
 HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
+DENOISE_FEAT, DENOISE_LEVELS = 32, 4                     # latent size / UNet levels of the denoise measurement (256x256 images)
 EXCHANGE = "NVLink copy engines in row chunks (smallest first) under the attention, K and V^T on two streams; grids <= 8x8 read the peer's K/V^T in-kernel (unicast TMA over NVLink); the whole step replays as one CUDA graph"
 
 
@@ -201,11 +202,12 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
     from cvd_b200 import sampler, sync_unet
     torch.manual_seed(0)
     np.random.seed(0)
-    net = sync_unet.SyncPathUNet().randomize_zero_init(1).to(dev).eval()
+    net = sync_unet.SyncPathUNet(levels=DENOISE_LEVELS).randomize_zero_init(1).to(dev).eval()
+    chans, ft = sync_unet.CHANNELS[:DENOISE_LEVELS], DENOISE_FEAT
     V_loc, V = 2, 2 * world
     g = torch.Generator(device=dev).manual_seed(42)
-    lat = torch.randn(V_loc, 4, 16, 32, 32, device=dev, generator=g)
-    poses = [torch.randn(V_loc, c, 16, 32 >> i, 32 >> i, device=dev, generator=g) for i, c in enumerate(sync_unet.CHANNELS)]
+    lat = torch.randn(V_loc, 4, 16, ft, ft, device=dev, generator=g)
+    poses = [torch.randn(V_loc, c, 16, ft >> i, ft >> i, device=dev, generator=g) for i, c in enumerate(chans)]
     sch = sampler.DDIMSchedule(device=dev)
     if world == 1:
         text = torch.randn(2, 77, 768, device=dev, generator=g)
@@ -261,8 +263,8 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
         try:
             V6 = 6
             g6 = torch.Generator(device=dev).manual_seed(43)
-            lat6 = torch.randn(V6, 4, 16, 32, 32, device=dev, generator=g6)
-            poses6 = [torch.randn(V6, c, 16, 32 >> i, 32 >> i, device=dev, generator=g6) for i, c in enumerate(sync_unet.CHANNELS)]
+            lat6 = torch.randn(V6, 4, 16, ft, ft, device=dev, generator=g6)
+            poses6 = [torch.randn(V6, c, 16, ft >> i, ft >> i, device=dev, generator=g6) for i, c in enumerate(chans)]
             text6 = torch.randn(2, 77, 768, device=dev, generator=g6).repeat(V6, 1, 1)
             c2w6, K6 = sampler.multiview_cameras(V6, 16, "upper_hemi", 0.5, 256)
 
@@ -291,8 +293,8 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
         # gather per UNet call) with all V views on this one GPU (R = 32 V rows), multistep = 1
         by_views = {"2": {"steps_per_s": 1e3 / (e0.elapsed_time(e1) / steps), "rows": 64, "launch": "one CUDA graph per UNet forward"}}
         for Vn, rig in ((4, "circle"), (6, "upper_hemi")):
-            lat_v = torch.randn(Vn, 4, 16, 32, 32, device=dev, generator=g)
-            poses_v = [torch.randn(Vn, c, 16, 32 >> i, 32 >> i, device=dev, generator=g) for i, c in enumerate(sync_unet.CHANNELS)]
+            lat_v = torch.randn(Vn, 4, 16, ft, ft, device=dev, generator=g)
+            poses_v = [torch.randn(Vn, c, 16, ft >> i, ft >> i, device=dev, generator=g) for i, c in enumerate(chans)]
             text_v = torch.randn(2, 77, 768, device=dev, generator=g).repeat(Vn, 1, 1)
             c2w, K = sampler.multiview_cameras(Vn, 16, rig, 0.5, 256)
 

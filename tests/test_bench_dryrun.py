@@ -194,3 +194,45 @@ def test_bench_sharded_run_control_flow(monkeypatch):
     assert d["gpu_launches"] == 2 * (4 + 3 + 3 + 1 + 1), d["gpu_launches"]
     assert d["roofline"]["ms_per_launch"] == 3.0            # three chunk launches of 1.0 "ms" each add up to one call
     assert "roofline_by_shape" not in d and "reference_gpu" not in d      # N = 1 extras only
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_denoise_bench_control_flow(monkeypatch, world):
+    """``bench.denoise_bench`` at reduced size (4x4 latents, one UNet level): N = 1 -- the graphed two-video loop and the
+    2 / 4 / 6-view triple; N = 2 (one process pretending to be rank 0 of 2, peers aliased) -- the view-sharded loop and the
+    unit-sharded config-4 loop (6 views x 2 x 2 = 24 units, 12 per rank), each with its guarded error reporting."""
+    import numpy as np
+    import torch.distributed as dist
+    fake_cuda(monkeypatch)
+    emulated_ops.install(monkeypatch)
+    from cvd_b200 import ops
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "DENOISE_FEAT", 4)
+    monkeypatch.setattr(bench, "DENOISE_LEVELS", 1)
+    shard = peer = None
+    if world > 1:
+        monkeypatch.setattr(dist, "get_world_size", lambda group=None: world)
+        monkeypatch.setattr(dist, "get_rank", lambda group=None: 0)
+        monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
+        monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: None)
+        from cvd_b200 import sharding
+        shard = sharding.ViewShard()
+
+        class AliasPeer:
+            mode = "hidden"
+
+            def exchange(self, x, partner):
+                return x[(partner.long() % x.shape[0])].contiguous()
+
+            def identity_index(self, n, device):
+                return torch.arange(n, device=device, dtype=torch.int32)
+        peer = AliasPeer()
+    ms, views, ms_eager, by_views = bench.denoise_bench(torch.device("cpu"), world, 0, shard, peer, 2)
+    assert ms == 0.5 and views == 2 * world            # fake events: 1.0 "ms" over 2 steps
+    if world == 1:
+        assert ms_eager == 0.5 and set(by_views) == {"2", "4", "6"} and by_views["6"]["rows"] == 192
+    else:
+        assert "error" not in by_views["config4"], by_views["config4"]
+        assert by_views["config4"]["units_per_gpu"] == 12 and by_views["config4"]["views"] == 6 and by_views["config4"]["finite"]
