@@ -90,6 +90,40 @@ def epi_attn_fwd_sharded(q, k_srcs, vt_srcs, rows_per_src, rowp, partner, heads,
     return _attend(q, torch.cat(list(k_srcs)), torch.cat(list(vt_srcs)), rowp, partner, heads, F_mat_size)
 
 
+def _logits_and_values(q, k_all, v_all, rowp, partner, heads, F_mat_size):
+    """fp32 [R,H,N,M] logits (natural log units) and [R,H,M,d] values of the single-partner training path."""
+    R, N, C = q.shape
+    d = C // heads
+    idx = partner.long()
+    qh = q.float().view(R, N, heads, d).transpose(1, 2)
+    kh = k_all.float()[idx].view(R, N, heads, d).transpose(1, 2)
+    vh = v_all.float()[idx].view(R, N, heads, d).transpose(1, 2)
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * d ** -0.5
+    if rowp is not None:
+        s = s + epi_bias_dense(rowp, int(round(N ** 0.5)), F_mat_size)[:, None]
+    return s, vh
+
+
+def epi_attn_fwd_lse(q, k, vt, rowp, partner, heads, F_mat_size):
+    out = epi_attn_fwd(q, k, vt, rowp, partner, heads, F_mat_size)
+    d = q.shape[2] // heads
+    v = vt[:, :, :d].transpose(-1, -2).reshape(vt.shape[0], heads, q.shape[1], d).transpose(1, 2).reshape(vt.shape[0], q.shape[1], -1)
+    s, _ = _logits_and_values(q, k, v, rowp, partner, heads, F_mat_size)
+    return out, (torch.logsumexp(s, dim=-1) * 1.4426950408889634).contiguous()        # base-2 log-sum-exp [R,H,N]
+
+
+def epi_attn_bwd(q, k, v, rowp, partner, out, d_out, lse, heads, F_mat_size):
+    """fp32 (dq, dk, dv) of out = softmax(q k[partner]^T / sqrt(d) + bias) v[partner]: torch autograd through the fp32
+    restatement (the kernel recomputes P from lse; the contract is the gradient)."""
+    R, N, C = q.shape
+    qf, kf, vf = (t_.detach().float().requires_grad_(True) for t_ in (q, k, v))
+    with torch.enable_grad():
+        s, vh = _logits_and_values(qf, kf, vf, rowp, partner, heads, F_mat_size)
+        o = torch.matmul(torch.softmax(s, dim=-1), vh).transpose(1, 2).reshape(R, N, C)
+        o.backward(d_out.float())
+    return qf.grad, kf.grad, vf.grad
+
+
 def groupnorm_tokens(x, gamma, beta, groups=32, eps=1e-6, layout=0):
     B, C, Fr, h, w = x.shape
     xt = x.float().permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w)
@@ -179,7 +213,7 @@ def plucker_embedding(intrinsics, c2w, H, W, flip_flag=None, channel_major=True)
     return out.permute(0, 3, 1, 2).contiguous() if channel_major else out
 
 
-EMULATED = ["epi_row_params", "epi_bias_dense", "epi_attn_fwd", "epi_attn_fwd_sharded", "groupnorm_tokens", "layernorm",
+EMULATED = ["epi_row_params", "epi_bias_dense", "epi_attn_fwd", "epi_attn_fwd_sharded", "epi_attn_fwd_lse", "epi_attn_bwd", "groupnorm_tokens", "layernorm",
             "residual_layernorm_", "geglu", "residual_add_", "tokens_to_video", "temporal_attn", "add_pose_tokens", "scale_add",
             "pairwise_fundamental", "plucker_embedding"]
 

@@ -310,3 +310,58 @@ def test_unit_loop_through_real_layers_sharded_world2(monkeypatch):
         # bf16 GEMMs over 4 units per rank instead of 8: rounding noise 6e-3 (a wrong pairing: 9e-2, see the test above)
         assert rel_l2(torch.from_numpy(ret[r]), ref) < 2e-2, (r, rel_l2(torch.from_numpy(ret[r]), ref))
     assert np.array_equal(ret[0], ret[1])          # every rank holds the same replicated latents
+
+
+def test_training_step_host_logic_vs_oracle_autograd(golden, monkeypatch):
+    """The training path's host code on the CPU (kernels emulated): one EpiModule forward + backward in train() mode against
+    torch autograd through the fp32 oracle -- forward, d/dx and every parameter gradient (tests/test_gpu_training.py holds
+    the same comparison on the B200) -- and a backward through a SyncPathUNet level (temporal + epi sites, pose features)."""
+    import cvd_b200
+    from cvd_b200 import sync_unet
+    from oracle import epi_oracle as O
+    emulated_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))     # the train twins refuse CPU tensors
+    C, feat, B = 320, 4, 2
+    sd = gi.module_state_dict(C, 4100)
+    x = gi.hidden_video(B, C, 16, feat, feat, 4101)
+    wgt = gi.hidden_video(B, C, 16, feat, feat, 4102)
+    Fm = t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3)
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x_ref = x.clone().requires_grad_(True)
+    y_ref, _ = O.epi_module(x_ref, sd_ref, 8, Fm, 256)
+    (y_ref * wgt).sum().backward()
+    m = cvd_b200.EpiModule(C, num_attention_heads=8, num_transformer_block=1, attention_block_types=["Epi_Self", "Epi_Self"],
+                           epi_position_encoding=True, epi_position_encoding_feat_max_size=64,
+                           epi_position_encoding_F_mat_size=256, epi_rand_slope_ff=False, zero_initialize=True)
+    m.load_state_dict(sd, strict=False)
+    m.train()
+    xp = x.clone().requires_grad_(True)
+    y, aux = m(xp, F_mats=Fm)
+    (y * wgt).sum().backward()
+    assert len(aux) == 2 and aux[0]["query"].requires_grad
+    assert rel_l2(y.detach() - x, y_ref.detach() - x) < 3e-2 and rel_l2(xp.grad, x_ref.grad) < 5e-2
+    params = dict(m.named_parameters())
+    worst = max(rel_l2(params[n].grad, r.grad) for n, r in sd_ref.items())
+    assert worst < 5e-2, worst
+    # H_mats batches and batches without any matrix train too (train_epi_control.py:532-545)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bias_pseudo.npz"))
+    for kw in (dict(H_mats=t(g["H"]).reshape(2, 16, 3, 3)), dict()):
+        m.zero_grad()
+        y2, _ = m(x.clone().requires_grad_(True), **kw)
+        y2.float().pow(2).mean().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # backward through temporal + epi sites
+    torch.manual_seed(11)
+    net = sync_unet.SyncPathUNet(levels=1, epi_kwargs=dict(sync_unet.EPI_KWARGS, epi_rand_slope_ff=False)).randomize_zero_init(11)
+    for n_, p in net.named_parameters():
+        p.requires_grad_("epi" in n_)
+    net.train()
+    gen = torch.Generator().manual_seed(5)
+    lat = torch.randn(2, 4, 16, 4, 4, generator=gen)
+    out = net(lat, 481, F_mats=Fm, encoder_hidden_states=torch.randn(2, 77, 768, generator=gen),
+              pose_embedding_features=[torch.randn(2, 320, 16, 4, 4, generator=gen) * 0.5])
+    out.float().pow(2).mean().backward()
+    grads = [p.grad for n_, p in net.named_parameters() if p.requires_grad]
+    assert grads and all(g_ is not None and torch.isfinite(g_).all() for g_ in grads)
+    first_q = [p.grad for n_, p in net.named_parameters() if p.requires_grad and "to_q" in n_][0]
+    assert float(first_q.abs().max()) > 0
