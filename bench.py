@@ -315,6 +315,115 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
     return e0.elapsed_time(e1) / steps, V, ms_eager, by_views
 
 
+# SD-1.5 + AnimateDiff v3 + CameraCtrl + CVD: the UNet of configs/inference_config.yaml (unet_additional_kwargs) on top of the
+# SD-1.5 config.json (block_out_channels, cross_attention_dim 768, 8 heads, 2 layers per block)
+FULL_UNET_KWARGS = dict(
+    sample_size=32, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+    cross_attention_dim=768, attention_head_dim=8, norm_num_groups=32,
+    use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=False, motion_module_type="Vanilla",
+    motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+                              temporal_position_encoding=True, temporal_position_encoding_max_len=32,
+                              temporal_attention_dim_div=1, zero_initialize=False),
+    use_epi_module=True, epi_module_resolutions=(1, 2, 4, 8), epi_module_mid_block=False,
+    epi_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Epi_Self", "Epi_Self"],
+                           epi_position_encoding=True, epi_position_encoding_feat_max_size=64,
+                           epi_position_encoding_F_mat_size=256, epi_rand_slope_ff=True, zero_initialize=True))
+FULL_UNET_TEXT_LEN = 77
+
+
+def full_unet_bench(dev, steps):
+    """BASELINE metric (ii) on the WHOLE UNet: denoising steps/s of the two-video loop
+    (sampler.sample_pair: CFG batch of 4 videos = 64 rows at 32x32 latents, 256x256 images) on
+    cvd_b200.unet.UNet3DConditionModelPoseCond -- SD-1.5 spatial blocks (library convolutions / GEMMs under bf16 autocast)
+    with this package's motion and epi modules, random-init weights (zero-initialised pieces re-initialised so that the sync
+    path is visible), one CUDA graph per UNet forward -- and, beside it, ONE forward of the reference's own PyTorch GPU path
+    on the same parameter tree: the same UNet class in eager fp32 with oracle-backed motion / epi modules
+    (oracle/module_twins.py: dense bias per call, mask x 8 heads, plain softmax attention)."""
+    import cvd_b200
+    from cvd_b200 import sampler
+    from cvd_b200.unet import UNet3DConditionModelPoseCond
+    from oracle import module_twins
+    ch = FULL_UNET_KWARGS["block_out_channels"]
+    ft = FULL_UNET_KWARGS["sample_size"]
+    proc = dict(add_spatial=False, spatial_attn_names="attn1", add_temporal=True, temporal_attn_names="0",
+                pose_feature_dimensions=list(ch), query_condition=True, key_value_condition=True, scale=1.0,
+                add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False)
+    torch.manual_seed(0)
+    net = UNet3DConditionModelPoseCond(**FULL_UNET_KWARGS)
+    net.set_all_attn_processor(**proc)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for name, p in net.named_parameters():      # zero_initialize / qkv_merge: visible in a random-init run
+            if (name.endswith("proj_out.weight") and "epi_modules" in name) or name.endswith("qkv_merge.weight"):
+                p.copy_(torch.randn(p.shape, generator=g) * (0.5 / p.shape[1] ** 0.5))
+    net = net.to(dev).eval()
+    n_params = sum(p.numel() for p in net.parameters())
+    gd = torch.Generator(device=dev).manual_seed(42)
+    lat = torch.randn(2, 4, 16, ft, ft, device=dev, generator=gd)
+    text = torch.randn(2, FULL_UNET_TEXT_LEN, FULL_UNET_KWARGS["cross_attention_dim"], device=dev, generator=gd)
+    poses = [torch.randn(2, c, 16, ft >> i, ft >> i, device=dev, generator=gd) * 0.5 for i, c in enumerate(ch)]
+    Fm = golden_F().reshape(2, 16, 3, 3).to(dev)
+    sch = sampler.DDIMSchedule(device=dev)
+    gnet = cvd_b200.GraphedModule(net)
+
+    def unet(x, t, **kw):
+        return gnet(x, torch.full((), float(t), device=dev), **kw)
+
+    def run(n, fn):
+        return sampler.sample_pair(fn, lat, Fm, text, sch, n, 8.5, pose_embedding_features=poses)
+    out = {"unet": "cvd_b200.unet.UNet3DConditionModelPoseCond, SD-1.5 + AnimateDiff v3 + CameraCtrl + CVD layout, random init",
+           "parameters_M": n_params / 1e6, "views": 2, "rows": 64, "sd_blocks": "bf16 autocast (cuDNN / cuBLAS / SDPA)"}
+    with torch.no_grad():
+        run(2, unet)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        res = run(steps, unet)
+        b.record()
+        torch.cuda.synchronize()
+        assert torch.isfinite(res).all()
+        out["ms_per_step"] = a.elapsed_time(b) / steps
+        out["steps_per_s"] = 1e3 / out["ms_per_step"]
+        out["launch"] = "one CUDA graph per UNet forward"
+        # the reference's own PyTorch GPU path on the same weights: eager fp32, oracle-backed sync / temporal modules
+        twin = UNet3DConditionModelPoseCond(**dict(FULL_UNET_KWARGS, amp=False), **module_twins.unet_factories())
+        twin.set_all_attn_processor(**proc)
+        twin.load_state_dict(net.state_dict(), strict=False)
+        twin = twin.to(dev).eval()
+        for blk in twin.modules():                   # the twin's epi modules use the horizontal first-frame rule
+            if hasattr(blk, "rand_slope_on_first_frame"):
+                blk.rand_slope_on_first_frame = False
+        x4 = torch.cat([lat[:1], lat[:1], lat[1:], lat[1:]])
+        F4 = torch.cat([Fm[:1], Fm[:1], Fm[1:], Fm[1:]])
+        t4 = text.repeat(2, 1, 1)
+        p4 = [torch.cat([x[:1], x[:1], x[1:], x[1:]]) for x in poses]
+        with torch.device(dev):
+            y_ref = twin(x4, 481, encoder_hidden_states=t4, F_mats=F4, pose_embedding_features=p4).sample
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(2):
+                y_ref = twin(x4, 481, encoder_hidden_states=t4, F_mats=F4, pose_embedding_features=p4).sample
+            b.record()
+            torch.cuda.synchronize()
+        ms_ref = a.elapsed_time(b) / 2
+        for m_ in net.modules():                     # same first-frame rule on both sides for the difference below
+            if hasattr(m_, "rand_slope_on_first_frame"):
+                m_.rand_slope_on_first_frame = False
+        y_our = net(x4, 481, encoder_hidden_states=t4, F_mats=F4, pose_embedding_features=p4).sample
+        a.record()
+        for _ in range(3):
+            y_our = net(x4, 481, encoder_hidden_states=t4, F_mats=F4, pose_embedding_features=p4).sample
+        b.record()
+        torch.cuda.synchronize()
+        ms_eager = a.elapsed_time(b) / 3
+        out["forward"] = {"reference_gpu_fp32_eager_ms": ms_ref, "ours_eager_ms": ms_eager,
+                          "ours_graphed_ms": out["ms_per_step"], "speedup_vs_reference_gpu": ms_ref / out["ms_per_step"],
+                          "rel_l2": float((y_our.double() - y_ref.double()).norm() / y_ref.double().norm())}
+    return out
+
+
 def extras_single_gpu(dev, peak_bw, F_rows):
     """Two more measurements for the N = 1 line, each guarded (a failure is reported in the line, never fatal):
 
@@ -691,9 +800,14 @@ def run_ours(args):
     torch.cuda.empty_cache()
     ms_denoise, views, ms_eager, by_views = (None, 0, None, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
 
-    glue_rows = ref_gpu = None
+    glue_rows = ref_gpu = full_unet = None
     if world == 1 and not args.no_extras:
         glue_rows, ref_gpu = extras_single_gpu(dev, peak_bw, F_rows)
+        if not args.no_denoise:
+            try:
+                full_unet = full_unet_bench(dev, max(2, min(args.steps, 3)))
+            except Exception as exc:
+                full_unet = {"error": f"{type(exc).__name__}: {exc}"}
 
     # max over ranks
     if world > 1:
@@ -741,6 +855,8 @@ def run_ours(args):
                                "loop": "sampler.sample_pair" if world == 1 else "sampler.sample_multiview (view-sharded)"}
             if by_views is not None:
                 line["denoise"]["by_views"] = by_views
+            if full_unet is not None:
+                line["denoise"]["full_unet"] = full_unet
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -20,5 +20,6 @@ from .motion_module import (AttnProcessor, PoseAdaptorAttnProcessor, PositionalE
                             get_motion_module)
 
 from .pose_encoder import CameraPoseEncoder  # noqa: F401
+from .unet import UNet3DConditionModelPoseCond  # noqa: F401
 
 __version__ = "0.2.0"

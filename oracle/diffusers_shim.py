@@ -134,6 +134,11 @@ class Attention(nn.Module):
             self._modules.pop("processor")
         self.processor = processor
 
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
+        """diffusers: ``Attention.forward`` hands everything to the installed processor."""
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **cross_attention_kwargs)
+
     def prepare_attention_mask(self, attention_mask, target_length, batch_size, out_dim=3):
         head_size = self.heads
         if attention_mask is None:
@@ -231,17 +236,19 @@ def install():
 
     root = mod("diffusers", _cvd_b200_shim=True)
     root.__path__ = []
-    mod("diffusers.utils", BaseOutput=BaseOutput, USE_PEFT_BACKEND=USE_PEFT_BACKEND)
+    from . import diffusers_unet_shim as U        # the UNet-level classes (imports this module: keep the import local)
+    mod("diffusers.utils", BaseOutput=BaseOutput, USE_PEFT_BACKEND=USE_PEFT_BACKEND, logging=U.logging,
+        SAFETENSORS_WEIGHTS_NAME="diffusion_pytorch_model.safetensors")
     models = mod("diffusers.models")
     models.__path__ = []
-    mod("diffusers.models.attention_processor", Attention=Attention, SpatialNorm=_Placeholder)
+    mod("diffusers.models.attention_processor", Attention=Attention, SpatialNorm=_Placeholder, AttentionProcessor=object,
+        LoRAAttnProcessor=_Placeholder, AttnProcessor2_0=AttnProcessor2_0)
     mod("diffusers.models.attention", Attention=Attention, FeedForward=FeedForward,
-        BasicTransformerBlock=_Placeholder)
+        BasicTransformerBlock=U.BasicTransformerBlock)
     mod("diffusers.models.lora", LoRALinearLayer=LoRALinearLayer)
     mod("diffusers.models.activations", get_activation=lambda name: nn.SiLU(), GEGLU=GEGLU)
     mod("diffusers.models.normalization", AdaGroupNorm=_Placeholder)
-    mod("diffusers.models.resnet", ResnetBlock2D=_Placeholder)
-    mod("diffusers.models.transformer_2d", Transformer2DModel=_Placeholder)
+    U.register(mod)
     for name in ("decord", "imageio"):
         if name not in sys.modules:
             try:

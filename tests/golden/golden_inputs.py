@@ -178,3 +178,31 @@ def fill_state_dict(shapes, seed):
 def plucker_like(B, H, W, seed, frames=16):
     rs = np.random.RandomState(seed)
     return torch.from_numpy(rs.standard_normal((B, 6, frames, H, W)).astype(np.float32))
+
+
+# ---- full UNet wiring (unet.py / unet_blocks.py) at a reduced width: every block kind, two resolutions --------------------
+UNET_MOTION_KWARGS = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Temporal_Self", "Temporal_Self"],
+                          temporal_position_encoding=True, temporal_position_encoding_max_len=32, temporal_attention_dim_div=1,
+                          zero_initialize=False)
+UNET_EPI_KWARGS = dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=["Epi_Self", "Epi_Self"],
+                       epi_position_encoding=True, epi_position_encoding_feat_max_size=64, epi_position_encoding_F_mat_size=256,
+                       epi_rand_slope_ff=False, zero_initialize=True)
+UNET_KWARGS = dict(sample_size=8, in_channels=4, out_channels=4, block_out_channels=(32, 64),
+                   down_block_types=("CrossAttnDownBlock3D", "DownBlock3D"), up_block_types=("UpBlock3D", "CrossAttnUpBlock3D"),
+                   layers_per_block=1, cross_attention_dim=48, attention_head_dim=8, norm_num_groups=8,
+                   use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=False,
+                   motion_module_type="Vanilla", motion_module_kwargs=UNET_MOTION_KWARGS,
+                   use_epi_module=True, epi_module_resolutions=(1, 2, 4, 8), epi_module_mid_block=False,
+                   epi_module_kwargs=UNET_EPI_KWARGS)
+UNET_PROCESSOR_KWARGS = dict(add_spatial=False, spatial_attn_names="attn1", add_temporal=True, temporal_attn_names="0",
+                             pose_feature_dimensions=[32, 64], query_condition=True, key_value_condition=True, scale=1.0)
+UNET_SEED = 8800
+
+
+def unet_inputs(seed=UNET_SEED, feat=8):
+    rs = np.random.RandomState(seed + 1)
+    lat = torch.from_numpy(rs.standard_normal((2, 4, 16, feat, feat)).astype(np.float32))
+    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, 48))).astype(np.float32))
+    poses = [torch.from_numpy((0.5 * rs.standard_normal((2, c, 16, feat >> i, feat >> i))).astype(np.float32))
+             for i, c in enumerate((32, 64))]
+    return lat, text, poses

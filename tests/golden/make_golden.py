@@ -276,6 +276,44 @@ def pose_encoder():
     save("pose_encoder", **out)
 
 
+def unet(Fm):
+    """The reference's UNet3DConditionModelPoseCond (models/unet.py, unet_blocks.py run verbatim on the restated diffusers
+    blocks of oracle/diffusers_unet_shim.py) at a reduced width: parameter table, two forward passes, and the final latents
+    of a 4-step two-video DDIM run (the oracle's restatement of pipeline_animation_epi.py:563-656 driving the reference
+    UNet, guidance 4.0)."""
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    from oracle import sampler_oracle as SO
+    m = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    m.eval()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    missing, unexpected = m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_SEED), strict=False)
+    assert not unexpected and all(k.endswith(skip) for k in missing), (missing, unexpected)
+    lat, text, poses = gi.unet_inputs()
+    F2 = Fm.reshape(2, 16, 3, 3)
+    out = {"names": np.array(sorted(shapes)), "shapes": np.array([str(shapes[k]) for k in sorted(shapes)])}
+    for t in (481, 21):
+        out[f"sample_t{t}"] = m(lat, t, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample
+    # without F matrices the epi modules fall back to random pseudo lines (epi_module.py:317-320): one torch.rand([rows]) per
+    # epi attention call from the global generator -- seeded here so that the product's RNG consumption can be checked
+    torch.manual_seed(1234)
+    out["sample_nopose_noF"] = m(lat, 481, encoder_hidden_states=text).sample
+
+    def call(x, t, F_mats=None, encoder_hidden_states=None, pose_embedding_features=None):
+        return m(x, t, encoder_hidden_states=encoder_hidden_states, F_mats=F_mats,
+                 pose_embedding_features=pose_embedding_features).sample
+    text2 = torch.cat([text * 0.0, text], dim=0)[[0, 2]]          # (uncond, cond) of one prompt, as the pipeline batches it
+    out["ddim_text"] = text2
+    out["ddim_final"] = SO.sample_pair(lambda x, t, **kw: call(x, t, kw.get("F_mats"), kw.get("encoder_hidden_states"),
+                                                               kw.get("pose_embedding_features")),
+                                       lat.clone(), F2, text2, 4, 4.0, pose_features=poses)
+    save("unet", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -297,7 +335,10 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet"):
+        if sys.argv[1] == "unet":
+            unet(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
+            sys.exit(0)
         {"plucker": plucker, "bias_pseudo": bias_pseudo, "pose_encoder": pose_encoder}[sys.argv[1]]()
         sys.exit(0)
     Fm = geometry()
@@ -309,3 +350,4 @@ if __name__ == "__main__":
     plucker()
     bias_pseudo()
     pose_encoder()
+    unet(Fm)

@@ -236,3 +236,22 @@ def test_denoise_bench_control_flow(monkeypatch, world):
     else:
         assert "error" not in by_views["config4"], by_views["config4"]
         assert by_views["config4"]["units_per_gpu"] == 12 and by_views["config4"]["views"] == 6 and by_views["config4"]["finite"]
+
+
+def test_full_unet_bench_control_flow(monkeypatch):
+    """``bench.full_unet_bench`` (whole-UNet denoise steps/s + the reference-GPU twin beside it) at the reduced width of the
+    UNet fixtures: graphed loop, twin construction with oracle-backed modules on the same state dict, the difference
+    between the two noise predictions (bf16-emulated sync path vs the fp32 oracle: a few 1e-3)."""
+    import golden_inputs as gi
+    fake_cuda(monkeypatch)
+    emulated_ops.install(monkeypatch)
+    from cvd_b200 import ops
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    sys.path.insert(0, ROOT)
+    import bench
+    kw = dict(gi.UNET_KWARGS, amp=False)             # fp32 SD blocks on the CPU (bf16 autocast convolutions are slow there)
+    monkeypatch.setattr(bench, "FULL_UNET_KWARGS", kw)
+    monkeypatch.setattr(bench, "FULL_UNET_TEXT_LEN", 7)
+    out = bench.full_unet_bench(torch.device("cpu"), 2)
+    assert out["steps_per_s"] == 2000.0 and out["views"] == 2 and out["parameters_M"] > 1.0
+    assert out["forward"]["rel_l2"] < 2e-2, out["forward"]

@@ -365,3 +365,63 @@ def test_training_step_host_logic_vs_oracle_autograd(golden, monkeypatch):
     assert grads and all(g_ is not None and torch.isfinite(g_).all() for g_ in grads)
     first_q = [p.grad for n_, p in net.named_parameters() if p.requires_grad and "to_q" in n_][0]
     assert float(first_q.abs().max()) > 0
+
+
+# ---- the full UNet (SD-1.5 blocks + motion + epi modules) against the reference's own wiring ---------------------------
+def _product_unet():
+    import cvd_b200
+    from cvd_b200.unet import UNet3DConditionModelPoseCond
+    m = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS, amp=False)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    return m.eval()
+
+
+def test_unet_state_dict_contract_and_forward_vs_reference(golden, monkeypatch):
+    """cvd_b200.unet.UNet3DConditionModelPoseCond against the REFERENCE's UNet3DConditionModelPoseCond (models/unet.py and
+    unet_blocks.py executed verbatim behind the shim, tests/golden/unet.npz): identical parameter names and shapes (the
+    checkpoint contract), and the same output for two timesteps with F matrices + pose features and for a call without
+    either (sync path off).  SD blocks in fp32 here (amp=False); sync / temporal kernels emulated."""
+    emulated_ops.install(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    m = _product_unet()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    assert sorted(mine) == g["names"].tolist()
+    assert [str(mine[k]) for k in sorted(mine)] == g["shapes"].tolist()
+    missing, unexpected = m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    assert not unexpected and all(k.endswith(skip) for k in missing)
+    lat, text, poses = gi.unet_inputs()
+    F2 = t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3)
+    with torch.no_grad():
+        for ts in (481, 21):
+            out = m(lat, ts, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample
+            assert rel_l2(out, t(g[f"sample_t{ts}"])) < REL, (ts, rel_l2(out, t(g[f"sample_t{ts}"])))
+        # no F matrices: random pseudo lines on every row, drawn from the global generator in the reference's order
+        torch.manual_seed(1234)
+        out = m(lat, torch.tensor(481), encoder_hidden_states=text).sample
+        assert rel_l2(out, t(g["sample_nopose_noF"])) < REL
+
+
+def test_fixed_seed_ddim_final_latents_vs_reference_unet(golden, monkeypatch):
+    """North star: "final latents after a fixed-seed DDIM run with random-init weights" -- the product's two-video loop
+    (sampler.sample_pair) driving the product UNet, against the oracle restatement of the reference loop
+    (pipeline_animation_epi.py:563-656) driving the REFERENCE UNet (fixture ``ddim_final``): 4 DDIM steps, guidance 4.0,
+    CFG batch of 4 videos, pose features and F matrices on.  Stated tolerance 5e-2 (bf16 GEMM operands inside the sync /
+    temporal modules against the reference's fp32, amplified by guidance over four steps)."""
+    from cvd_b200 import sampler
+    emulated_ops.install(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    m = _product_unet()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    lat, _text, poses = gi.unet_inputs()
+    F2 = t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3)
+    with torch.no_grad():
+        final = sampler.sample_pair(m, lat.clone(), F2, t(g["ddim_text"]), sampler.DDIMSchedule(), 4, 4.0,
+                                    pose_embedding_features=poses)
+    err = rel_l2(final, t(g["ddim_final"]))
+    assert torch.isfinite(final).all() and err < 5e-2, err

@@ -21,36 +21,10 @@ def dev():
 
 def oracle_factories():
     """Factories for a CPU twin of SyncPathUNet: same parameter containers (product classes, never run), forward =
-    the CPU oracle's functional restatement on this module's own state_dict."""
-    import cvd_b200
+    the CPU oracle's functional restatement on this module's own state_dict (oracle/module_twins.py)."""
     from cvd_b200 import sync_unet
-    from oracle import epi_oracle as O
-
-    class OracleEpi(cvd_b200.EpiModule):
-        def forward(self, hidden_states, F_mats=None, H_mats=None, temb=None, **kw):
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
-            return O.epi_module(hidden_states, sd, 8, F_mats, 256)
-
-    class OracleMotion(cvd_b200.VanillaTemporalModule):
-        def forward(self, hidden_states, temb=None, encoder_hidden_states=None, attention_mask=None,
-                    cross_attention_kwargs={}):
-            sd = {k: v.detach() for k, v in self.state_dict().items()}
-            p = "temporal_transformer.transformer_blocks.0.attention_blocks.0.processor.qkv_merge."
-            merges = [(sd[p + "weight"], sd[p + "bias"]), None]
-            return O.temporal_module(hidden_states, sd, 8, cross_attention_kwargs.get("pose_feature"), merges)
-
-    def epi_factory(c, kw):
-        return OracleEpi(in_channels=c, **kw)
-
-    def motion_factory(c, kw):
-        m = OracleMotion(in_channels=c, **kw)
-        blk = m.temporal_transformer.transformer_blocks[0]
-        blk.attention_blocks[0].set_processor(cvd_b200.PoseAdaptorAttnProcessor(
-            hidden_size=c, pose_feature_dim=c, query_condition=True, key_value_condition=True, scale=1.0))
-        blk.attention_blocks[1].set_processor(cvd_b200.AttnProcessor(attn_type="temporal"))
-        return m
-
-    return dict(epi_factory=epi_factory, motion_factory=motion_factory), sync_unet
+    from oracle import module_twins
+    return module_twins.sync_unet_factories(), sync_unet
 
 
 def build_pair(dev, levels, seed):
