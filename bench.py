@@ -351,8 +351,9 @@ def full_unet_bench(dev, steps):
                 motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
                 sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False)
     torch.manual_seed(0)
-    net = UNet3DConditionModelPoseCond(**FULL_UNET_KWARGS)
-    net.set_all_attn_processor(**proc)
+    with torch.device(dev):                          # parameters are created (and randomly initialised) on the device
+        net = UNet3DConditionModelPoseCond(**FULL_UNET_KWARGS)
+        net.set_all_attn_processor(**proc)
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         for name, p in net.named_parameters():      # zero_initialize / qkv_merge: visible in a random-init run
@@ -388,8 +389,9 @@ def full_unet_bench(dev, steps):
         out["steps_per_s"] = 1e3 / out["ms_per_step"]
         out["launch"] = "one CUDA graph per UNet forward"
         # the reference's own PyTorch GPU path on the same weights: eager fp32, oracle-backed sync / temporal modules
-        twin = UNet3DConditionModelPoseCond(**dict(FULL_UNET_KWARGS, amp=False), **module_twins.unet_factories())
-        twin.set_all_attn_processor(**proc)
+        with torch.device(dev):
+            twin = UNet3DConditionModelPoseCond(**dict(FULL_UNET_KWARGS, amp=False), **module_twins.unet_factories())
+            twin.set_all_attn_processor(**proc)
         twin.load_state_dict(net.state_dict(), strict=False)
         twin = twin.to(dev).eval()
         for blk in twin.modules():                   # the twin's epi modules use the horizontal first-frame rule
