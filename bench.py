@@ -585,7 +585,10 @@ def run_ours(args):
     #   16x16, d = 80: 296 slots, 16 CTAs per row -> 18.5 rows per wave.  Transfer-bound (68 us against 36 us): the step
     #     ends one chunk of attention after the LAST byte lands, so the last chunks are the small ones: 28 | 18 | 18.
     chunk_plan = {32: parse_chunks("CVD_BENCH_CHUNKS32", [9, 18, 37]), 16: parse_chunks("CVD_BENCH_CHUNKS16", [28, 18, 18])}
-    runs_of = None
+    # issued eagerly (graph capture failed or --no-graph) the host is the limiter and every extra chunk costs more than it
+    # hides (round 1, measured: three chunks 6.36 ms per step against 5.97 ms for two): the two-chunk plan of round 1
+    chunk_plan_eager = {32: parse_chunks("CVD_BENCH_CHUNKS32", [27, 37]), 16: parse_chunks("CVD_BENCH_CHUNKS16", [32, 32])}
+    runs_of = run_plan = run_plan_eager = None
     if shard is not None:
         # contiguous runs of the partner map inside [lo, hi): (dst_lo, dst_hi, source rank, source row)
         ph = partner.cpu().numpy()
@@ -600,6 +603,7 @@ def run_ours(args):
 
         partner_local = (partner % R).to(torch.int32)      # row inside the source rank's buffer
         run_plan = {f: [runs_of(lo, hi) for lo, hi in ch] for f, ch in chunk_plan.items()}
+        run_plan_eager = {f: [runs_of(lo, hi) for lo, hi in ch] for f, ch in chunk_plan_eager.items()}
         runs_whole = runs_of(0, R)
 
     def timed_attn(record, *a):
@@ -614,7 +618,8 @@ def run_ours(args):
         else:
             ops.epi_attn_fwd(*a)
 
-    def value_step(record):
+    def value_step(record, eager_plan=False):
+        chunks_of, runs_for = (chunk_plan_eager, run_plan_eager) if eager_plan else (chunk_plan, run_plan)
         main_stream = torch.cuda.current_stream()
         for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
             rec = record and feat == SHAPES[0][0]
@@ -641,7 +646,7 @@ def run_ours(args):
                     ev_b.record(main_stream)
                     side_k.wait_event(ev_b)
                     side_v.wait_event(ev_b)
-                    for c, runs_c in enumerate(run_plan[feat]):
+                    for c, runs_c in enumerate(runs_for[feat]):
                         with torch.cuda.stream(side_k):
                             for (dlo, dhi, src_rank, slo) in runs_c:
                                 ld[0][dlo:dhi].copy_(xk[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
@@ -650,7 +655,7 @@ def run_ours(args):
                             for (dlo, dhi, src_rank, slo) in runs_c:
                                 ld[1][dlo:dhi].copy_(xv[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
                             ev_v[c].record(side_v)
-                    for c, (lo, hi) in enumerate(chunk_plan[feat]):
+                    for c, (lo, hi) in enumerate(chunks_of[feat]):
                         main_stream.wait_event(ev_k[c])
                         main_stream.wait_event(ev_v[c])
                         timed_attn(rec, q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
@@ -703,7 +708,7 @@ def run_ours(args):
         if graph is not None:
             graph.replay()
         else:
-            value_step(True)
+            value_step(True, eager_plan=True)
     t1.record()
     barrier()
     launches = ops.LAUNCHES - launches0 if graph is None else launches_per_step * args.steps
@@ -713,6 +718,7 @@ def run_ours(args):
         for _ in range(2):
             value_step(True)
         barrier()
+    exchange_issue = ("one CUDA graph per step" if graph is not None else "eager") if world > 1 else None
     big_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in call) for call in big_events if call]))   # per call of R rows
 
     # every attention shape on its own (N = 1): the 10 calls of the shape back to back on their distinct buffers
@@ -842,6 +848,8 @@ def run_ours(args):
             "cpu_baseline": {"value": cb_val, "unit": "TFLOP/s", "cores": cores, "kind": "port",
                              "sample": f"oracle EpiSelfAttention.forward, 1 call per shape ({cb_flops / 1e9:.1f} GFLOP), best of 2"},
         }
+        if exchange_issue is not None:
+            line["config"]["exchange_issue"] = exchange_issue
         if by_shape is not None:
             line["roofline_by_shape"] = by_shape
         if glue_rows is not None:

@@ -125,7 +125,8 @@ def test_bench_reference_arm_honours_warmup(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
-def test_bench_sharded_run_control_flow(monkeypatch):
+@pytest.mark.parametrize("no_graph", [False, True])
+def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     """The N > 1 branch of ``run_ours`` in ONE process: rank 0 of a pretended world of 2 whose "peer" buffers alias its own
     (symmetric memory, the process group and the collectives replaced by stand-ins).  Exercises the chunk / run plans of
     the copy-engine exchange, the in-kernel branch of the small latents, the graph-capture path with its launch
@@ -183,16 +184,19 @@ def test_bench_sharded_run_control_flow(monkeypatch):
     monkeypatch.setattr(bench, "CALLS_PER_SHAPE", 1)
     monkeypatch.setattr(bench, "cpu_reference_step", lambda R, reps, warm: ([1.0] * reps, 1e9, 1))
     args = types.SimpleNamespace(gpus=2, steps=2, warmup=1, impl="ours", no_denoise=True, no_extras=False, exchange="dma",
-                                 no_graph=False)
+                                 no_graph=no_graph)
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
         bench.run_ours(args)
     d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][0])
     assert d["n_gpus"] == 2 and d["config"]["views_total"] == 4 and "copy engines" in d["config"]["parallelism"]
     assert all(t_ == sharding.BARRIER_TIMEOUT_MS for t_ in barriers) and len(barriers) > 0
-    # per step: 4 prepasses + 3 chunk launches (32x32) + 3 (16x16) + 1 + 1 in-kernel launches
-    assert d["gpu_launches"] == 2 * (4 + 3 + 3 + 1 + 1), d["gpu_launches"]
-    assert d["roofline"]["ms_per_launch"] == 3.0            # three chunk launches of 1.0 "ms" each add up to one call
+    # per step: 4 prepasses + the chunk launches of 32x32 and 16x16 (graph: 3 + 3 wave-sized chunks; eager: the two-chunk
+    # plan of round 1) + 1 + 1 in-kernel launches; the chunk launches of 1.0 "ms" each add up to one call
+    chunks = 2 if no_graph else 3
+    assert d["config"]["exchange_issue"] == ("eager" if no_graph else "one CUDA graph per step")
+    assert d["gpu_launches"] == 2 * (4 + 2 * chunks + 1 + 1), d["gpu_launches"]
+    assert d["roofline"]["ms_per_launch"] == float(chunks)
     assert "roofline_by_shape" not in d and "reference_gpu" not in d      # N = 1 extras only
 
 
