@@ -206,3 +206,15 @@ def unet_inputs(seed=UNET_SEED, feat=8):
     poses = [torch.from_numpy((0.5 * rs.standard_normal((2, c, 16, feat >> i, feat >> i))).astype(np.float32))
              for i, c in enumerate((32, 64))]
     return lat, text, poses
+
+
+def unet_multiview_inputs(V=4, seed=UNET_SEED + 50, feat=8):
+    """V-view inputs of the advanced pipeline at the UNet fixture's width: latents, CFG-interleaved text (U, C per view),
+    pose features of all views, and the re-noise tensors of the multistep repeats (drawn here, injected on both sides)."""
+    rs = np.random.RandomState(seed)
+    lat = torch.from_numpy(rs.standard_normal((V, 4, 16, feat, feat)).astype(np.float32))
+    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, 48))).astype(np.float32)).repeat(V, 1, 1)
+    poses = [torch.from_numpy((0.5 * rs.standard_normal((V, c, 16, feat >> i, feat >> i))).astype(np.float32))
+             for i, c in enumerate((32, 64))]
+    noises = [torch.from_numpy(rs.standard_normal((V, 4, 16, feat, feat)).astype(np.float32)) for _ in range(8)]
+    return lat, text, poses, noises

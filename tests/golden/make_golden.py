@@ -311,6 +311,16 @@ def unet(Fm):
     out["ddim_final"] = SO.sample_pair(lambda x, t, **kw: call(x, t, kw.get("F_mats"), kw.get("encoder_hidden_states"),
                                                                kw.get("pose_embedding_features")),
                                        lat.clone(), F2, text2, 4, 4.0, pose_features=poses)
+    # the V-view loop of the advanced pipeline (oracle restatement of pipeline_animation_epi_advanced.py:596-705) on the
+    # reference UNet: 4 views on the 'circle' rig, 3 DDIM steps, multistep 2 (re-noise), guidance 4.0, numpy seed 2024
+    from cvd_b200 import sampler as _s      # camera rig only (pinned to the reference's rig code by tests/golden/sampler.npz)
+    c2w, K = _s.multiview_cameras(4, 16, "circle", 0.5, 256)
+    lat4, text4, poses4, noises = gi.unet_multiview_inputs()
+    it = iter(noises)
+    np.random.seed(2024)
+    out["mv_final"] = SO.sample_multiview(
+        lambda x, t, **kw: call(x, t, kw.get("F_mats"), kw.get("encoder_hidden_states"), kw.get("pose_embedding_features")),
+        lat4.clone(), text4, 3, 4.0, c2w, K, poses4, multistep=2, accumulate=1, noise_fn=lambda shape: next(it))
     save("unet", **out)
 
 

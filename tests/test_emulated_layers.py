@@ -425,3 +425,27 @@ def test_fixed_seed_ddim_final_latents_vs_reference_unet(golden, monkeypatch):
                                     pose_embedding_features=poses)
     err = rel_l2(final, t(g["ddim_final"]))
     assert torch.isfinite(final).all() and err < 5e-2, err
+
+
+def test_multiview_ddim_final_latents_vs_reference_unet(monkeypatch):
+    """The V-view loop (pipeline_animation_epi_advanced.py:596-705) end to end: sampler.sample_multiview + the product UNet
+    (4 views, 'circle' rig, 3 DDIM steps with multistep 2 -> 5 CFG-batched UNet calls, per-call pairing from numpy's global
+    RNG, per-call F from the poses, kv_index gather, injected re-noise) against the oracle loop driving the REFERENCE UNet
+    (fixture ``mv_final``).  Tolerance 5e-2 (bf16 sync / temporal GEMM operands vs fp32, guidance 4.0, re-noising)."""
+    from cvd_b200 import ops, sampler
+    emulated_ops.install(monkeypatch)
+    monkeypatch.setattr(ops, "pairwise_fundamental", lambda c, k, partner: _host_F(c, k, partner.numpy().astype(np.int64)))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    m = _product_unet()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    lat4, text4, poses4, noises = gi.unet_multiview_inputs()
+    c2w, K = sampler.multiview_cameras(4, 16, "circle", 0.5, 256)
+    it = iter(noises)
+    np.random.seed(2024)
+    with torch.no_grad():
+        final = sampler.sample_multiview(m, lat4.clone(), text4, sampler.DDIMSchedule(), 3, 4.0, aux_c2w=c2w, aux_K_mats=K,
+                                         pose_embedding_features=poses4, multistep=2, noise_fn=lambda shape: next(it))
+    err = rel_l2(final, t(g["mv_final"]))
+    assert torch.isfinite(final).all() and err < 5e-2, err
