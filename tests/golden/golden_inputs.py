@@ -199,22 +199,30 @@ UNET_PROCESSOR_KWARGS = dict(add_spatial=False, spatial_attn_names="attn1", add_
 UNET_SEED = 8800
 
 
-def unet_inputs(seed=UNET_SEED, feat=8):
+# The same layout at the two narrowest widths of SD-1.5 (320, 640 -> head sizes 40 / 80 at 8x8 / 4x4 latents): the smallest
+# UNet whose sync / temporal modules have shapes the DEVICE kernels are instantiated for (the GPU parity tests use it; the
+# reduced-width configuration above only runs against the plain-torch test double).
+UNET_GPU_KWARGS = dict(UNET_KWARGS, block_out_channels=(320, 640), norm_num_groups=32, cross_attention_dim=64)
+UNET_GPU_PROCESSOR_KWARGS = dict(UNET_PROCESSOR_KWARGS, pose_feature_dimensions=[320, 640])
+UNET_GPU_SEED = 9900
+
+
+def unet_inputs(seed=UNET_SEED, feat=8, channels=(32, 64), text_dim=48):
     rs = np.random.RandomState(seed + 1)
     lat = torch.from_numpy(rs.standard_normal((2, 4, 16, feat, feat)).astype(np.float32))
-    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, 48))).astype(np.float32))
+    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, text_dim))).astype(np.float32))
     poses = [torch.from_numpy((0.5 * rs.standard_normal((2, c, 16, feat >> i, feat >> i))).astype(np.float32))
-             for i, c in enumerate((32, 64))]
+             for i, c in enumerate(channels)]
     return lat, text, poses
 
 
-def unet_multiview_inputs(V=4, seed=UNET_SEED + 50, feat=8):
+def unet_multiview_inputs(V=4, seed=UNET_SEED + 50, feat=8, channels=(32, 64), text_dim=48):
     """V-view inputs of the advanced pipeline at the UNet fixture's width: latents, CFG-interleaved text (U, C per view),
     pose features of all views, and the re-noise tensors of the multistep repeats (drawn here, injected on both sides)."""
     rs = np.random.RandomState(seed)
     lat = torch.from_numpy(rs.standard_normal((V, 4, 16, feat, feat)).astype(np.float32))
-    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, 48))).astype(np.float32)).repeat(V, 1, 1)
+    text = torch.from_numpy((0.5 * rs.standard_normal((2, 7, text_dim))).astype(np.float32)).repeat(V, 1, 1)
     poses = [torch.from_numpy((0.5 * rs.standard_normal((V, c, 16, feat >> i, feat >> i))).astype(np.float32))
-             for i, c in enumerate((32, 64))]
+             for i, c in enumerate(channels)]
     noises = [torch.from_numpy(rs.standard_normal((V, 4, 16, feat, feat)).astype(np.float32)) for _ in range(8)]
     return lat, text, poses, noises

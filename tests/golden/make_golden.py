@@ -324,6 +324,44 @@ def unet(Fm):
     save("unet", **out)
 
 
+def unet_gpu(Fm):
+    """The reference UNet at widths (320, 640) -- the shapes the device kernels are instantiated for -- for the GPU parity
+    tests: two forward passes and the final latents of a 4-step two-video DDIM run (guidance 4.0)."""
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    from oracle import sampler_oracle as SO
+    m = UNet3DConditionModelPoseCond(**gi.UNET_GPU_KWARGS)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_GPU_PROCESSOR_KWARGS)
+    m.eval()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    missing, unexpected = m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_GPU_SEED), strict=False)
+    assert not unexpected and all(k.endswith(skip) for k in missing), (missing, unexpected)
+    lat, text, poses = gi.unet_inputs(gi.UNET_GPU_SEED, channels=(320, 640), text_dim=64)
+    F2 = Fm.reshape(2, 16, 3, 3)
+    out = {"n_params": sum(int(np.prod(v)) for v in shapes.values())}
+    for t in (481, 21):
+        out[f"sample_t{t}"] = m(lat, t, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample
+    text2 = torch.cat([text * 0.0, text], dim=0)[[0, 2]]
+    out["ddim_text"] = text2
+    out["ddim_final"] = SO.sample_pair(
+        lambda x, t, **kw: m(x, t, encoder_hidden_states=kw.get("encoder_hidden_states"), F_mats=kw.get("F_mats"),
+                             pose_embedding_features=kw.get("pose_embedding_features")).sample,
+        lat.clone(), F2, text2, 4, 4.0, pose_features=poses)
+    from cvd_b200 import sampler as _s
+    c2w, K = _s.multiview_cameras(4, 16, "circle", 0.5, 256)
+    lat4, text4, poses4, noises = gi.unet_multiview_inputs(seed=gi.UNET_GPU_SEED + 50, channels=(320, 640), text_dim=64)
+    it = iter(noises)
+    np.random.seed(2024)
+    out["mv_final"] = SO.sample_multiview(
+        lambda x, t, **kw: m(x, t, encoder_hidden_states=kw.get("encoder_hidden_states"), F_mats=kw.get("F_mats"),
+                             pose_embedding_features=kw.get("pose_embedding_features")).sample,
+        lat4.clone(), text4, 3, 4.0, c2w, K, poses4, multistep=2, accumulate=1, noise_fn=lambda shape: next(it))
+    save("unet_gpu", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -348,6 +386,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet"):
         if sys.argv[1] == "unet":
             unet(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
+            unet_gpu(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
             sys.exit(0)
         {"plucker": plucker, "bias_pseudo": bias_pseudo, "pose_encoder": pose_encoder}[sys.argv[1]]()
         sys.exit(0)
@@ -361,3 +400,4 @@ if __name__ == "__main__":
     bias_pseudo()
     pose_encoder()
     unet(Fm)
+    unet_gpu(Fm)

@@ -449,3 +449,31 @@ def test_multiview_ddim_final_latents_vs_reference_unet(monkeypatch):
                                          pose_embedding_features=poses4, multistep=2, noise_fn=lambda shape: next(it))
     err = rel_l2(final, t(g["mv_final"]))
     assert torch.isfinite(final).all() and err < 5e-2, err
+
+
+def test_unet_device_shape_fixture_vs_reference(golden, monkeypatch):
+    """The fixture the GPU parity tests use (widths 320 / 640: the shapes the device kernels are instantiated for,
+    tests/golden/unet_gpu.npz) is reproduced by the product UNet with emulated kernels -- forward and the 4-step DDIM run --
+    so a failure of tests/test_gpu_zz_round2_late.py on the B200 points at the kernels, not at the host code or the fixture."""
+    from cvd_b200 import sampler
+    from cvd_b200.unet import UNet3DConditionModelPoseCond
+    emulated_ops.install(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_gpu.npz"))
+    m = UNet3DConditionModelPoseCond(**gi.UNET_GPU_KWARGS, amp=False)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_GPU_PROCESSOR_KWARGS)
+    m.eval()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    assert sum(int(np.prod(v)) for v in mine.values()) == int(g["n_params"])
+    m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_GPU_SEED), strict=False)
+    lat, text, poses = gi.unet_inputs(gi.UNET_GPU_SEED, channels=(320, 640), text_dim=64)
+    F2 = t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3)
+    with torch.no_grad():
+        out = m(lat, 481, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample
+        assert rel_l2(out, t(g["sample_t481"])) < REL
+        final = sampler.sample_pair(m, lat.clone(), F2, t(g["ddim_text"]), sampler.DDIMSchedule(), 4, 4.0,
+                                    pose_embedding_features=poses)
+    assert rel_l2(final, t(g["ddim_final"])) < 5e-2, rel_l2(final, t(g["ddim_final"]))

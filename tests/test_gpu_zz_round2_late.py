@@ -135,26 +135,28 @@ def test_pose_encoder_inference_path_vs_reference_fixture(dev, case):
 
 
 def _fixture_unet(dev, amp):
+    """The product UNet at widths (320, 640): the smallest configuration whose sync / temporal modules have shapes the
+    device kernels are instantiated for (head sizes 40 / 80 at 8x8 / 4x4 latents)."""
     from cvd_b200.unet import UNet3DConditionModelPoseCond
-    m = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS, amp=amp)
+    m = UNet3DConditionModelPoseCond(**gi.UNET_GPU_KWARGS, amp=amp)
     m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
                              motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
                              sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
-                             **gi.UNET_PROCESSOR_KWARGS)
+                             **gi.UNET_GPU_PROCESSOR_KWARGS)
     skip = ("pos_encoder.pe", "pos_encoder.coords")
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
-    m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_SEED), strict=False)
+    m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_GPU_SEED), strict=False)
     return m.to(dev).eval()
 
 
 @pytest.mark.parametrize("amp", [False, True])
 def test_unet_forward_vs_reference_unet_fixture(golden, dev, amp):
     """cvd_b200.unet.UNet3DConditionModelPoseCond on the device against the REFERENCE's UNet (models/unet.py +
-    unet_blocks.py executed verbatim, tests/golden/unet.npz): SD blocks fp32 (2e-2) and under bf16 autocast (4e-2)."""
+    unet_blocks.py executed verbatim, tests/golden/unet_gpu.npz): SD blocks fp32 (2e-2) and under bf16 autocast (4e-2)."""
     import os
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_gpu.npz"))
     m = _fixture_unet(dev, amp)
-    lat, text, poses = gi.unet_inputs()
+    lat, text, poses = gi.unet_inputs(gi.UNET_GPU_SEED, channels=(320, 640), text_dim=64)
     F2 = torch.from_numpy(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3).to(dev)
     with torch.no_grad():
         for ts in (481, 21):
@@ -166,33 +168,14 @@ def test_unet_forward_vs_reference_unet_fixture(golden, dev, amp):
 def test_fixed_seed_ddim_final_latents_vs_reference_unet_on_device(golden, dev):
     """North star: final latents of a fixed-seed DDIM run with random-init weights -- sampler.sample_pair + the product
     UNet on the B200 (SD blocks fp32, sync / temporal kernels through the C ABI) against the oracle loop driving the
-    REFERENCE UNet (fixture ``ddim_final``: 4 steps, guidance 4.0).  Stated tolerance 5e-2; 3.3e-3 with emulated kernels."""
+    REFERENCE UNet (fixture ``ddim_final`` of unet_gpu.npz: 4 steps, guidance 4.0).  Stated tolerance 5e-2."""
     import os
     from cvd_b200 import sampler
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_gpu.npz"))
     m = _fixture_unet(dev, False)
-    lat, _text, poses = gi.unet_inputs()
+    lat, _text, poses = gi.unet_inputs(gi.UNET_GPU_SEED, channels=(320, 640), text_dim=64)
     F2 = torch.from_numpy(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3).to(dev)
     with torch.no_grad():
         final = sampler.sample_pair(m, lat.to(dev), F2, torch.from_numpy(g["ddim_text"]).to(dev), sampler.DDIMSchedule(device=dev),
                                     4, 4.0, pose_embedding_features=[p.to(dev) for p in poses])
     assert_close(final, torch.from_numpy(g["ddim_final"]), rel=5e-2, what="ddim final latents")
-
-
-def test_multiview_ddim_final_latents_vs_reference_unet_on_device(dev):
-    """The V-view loop end to end on the B200 (sampler.sample_multiview + the product UNet: per-call pairing, device F
-    recompute, kv_index gather, injected re-noise; 4 views, 3 DDIM steps, multistep 2) against the oracle loop driving the
-    REFERENCE UNet (fixture ``mv_final``).  Tolerance 5e-2; 3.4e-3 with emulated kernels on the CPU."""
-    import os
-    from cvd_b200 import sampler
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
-    m = _fixture_unet(dev, False)
-    lat4, text4, poses4, noises = gi.unet_multiview_inputs()
-    c2w, K = sampler.multiview_cameras(4, 16, "circle", 0.5, 256)
-    it = iter(noises)
-    np.random.seed(2024)
-    with torch.no_grad():
-        final = sampler.sample_multiview(m, lat4.to(dev), text4.to(dev), sampler.DDIMSchedule(device=dev), 3, 4.0, aux_c2w=c2w,
-                                         aux_K_mats=K, pose_embedding_features=[p.to(dev) for p in poses4], multistep=2,
-                                         noise_fn=lambda shape: next(it).to(dev))
-    assert_close(final, torch.from_numpy(g["mv_final"]), rel=5e-2, what="multiview ddim final latents")
