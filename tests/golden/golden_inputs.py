@@ -154,6 +154,12 @@ POSE_ENCODER_CASES = [
                                      use_conv=True, compression_factor=1, temporal_attention_nhead=4,
                                      attention_block_types=["Temporal_Self"], temporal_position_encoding=False,
                                      temporal_position_encoding_max_len=16), B=1, H=16, W=24, seed=7200),
+    # the shipped configuration at the two narrowest SD-1.5 widths: the shapes the DEVICE kernels are instantiated for
+    # (LayerNorm widths 320 / 640, temporal attention head sizes 40 / 80) -- the case the GPU parity test runs
+    dict(name="pe_dev", kwargs=dict(downscale_factor=8, channels=[320, 640], nums_rb=2, cin=384, ksize=1, sk=True,
+                                    use_conv=False, compression_factor=1, temporal_attention_nhead=8,
+                                    attention_block_types=["Temporal_Self"], temporal_position_encoding=True,
+                                    temporal_position_encoding_max_len=16), B=2, H=32, W=32, seed=7300, device=True),
 ]
 
 
