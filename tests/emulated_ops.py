@@ -13,6 +13,18 @@ import torch.nn.functional as F
 
 BF = torch.bfloat16
 
+# ``install(..., strict_shapes=True)``: additionally refuse what the DEVICE kernels refuse (instantiated attention
+# configurations, LayerNorm widths, alignment rules of include/cvd_b200.h), so that a CPU test can prove that a model
+# configuration is runnable on the B200 before the GPU suite sees it.
+STRICT = {"on": False}
+_ATTN_TC = {(40, 32), (40, 64), (80, 16), (80, 32), (160, 16), (40, 16), (160, 8), (80, 8), (40, 8)}
+_ATTN_SMALL = {(160, 4), (80, 4), (40, 4)}
+
+
+def _strict(cond, what):
+    if STRICT["on"] and not cond:
+        raise AssertionError(f"the device kernel would refuse this call: {what}")
+
 
 def _pixel_centres(feat, S):
     step = S / feat
@@ -63,6 +75,7 @@ def _attend(q, k_all, vt_all, rowp, partner, heads, F_mat_size):
     d = C // heads
     kp = partner.shape[0] // R
     feat = int(round(N ** 0.5))
+    _strict((d, feat) in _ATTN_TC or ((d, feat) in _ATTN_SMALL and kp in (1, 2)), f"epi attention (head_dim={d}, feat={feat}, partners={kp})")
     qh = q.float().view(R, N, heads, d).transpose(1, 2)
     ss, vs = [], []
     for p in range(kp):
@@ -113,6 +126,8 @@ def epi_attn_fwd_lse(q, k, vt, rowp, partner, heads, F_mat_size):
 
 
 def epi_attn_bwd(q, k, v, rowp, partner, out, d_out, lse, heads, F_mat_size):
+    _strict(q.shape[2] // heads in (40, 80, 160) and q.shape[1] % 16 == 0 and partner.shape[0] == q.shape[0],
+            f"attention backward head_dim={q.shape[2] // heads} N={q.shape[1]}")
     """fp32 (dq, dk, dv) of out = softmax(q k[partner]^T / sqrt(d) + bias) v[partner]: torch autograd through the fp32
     restatement (the kernel recomputes P from lse; the contract is the gradient)."""
     R, N, C = q.shape
@@ -126,6 +141,7 @@ def epi_attn_bwd(q, k, v, rowp, partner, out, d_out, lse, heads, F_mat_size):
 
 def groupnorm_tokens(x, gamma, beta, groups=32, eps=1e-6, layout=0):
     B, C, Fr, h, w = x.shape
+    _strict(C % groups == 0 and C % 2 == 0 and B * Fr <= 65535, f"GroupNorm tokens C={C} groups={groups} B*F={B * Fr}")
     xt = x.float().permute(0, 2, 1, 3, 4).reshape(B * Fr, C, h, w)
     g = F.group_norm(xt, groups, gamma, beta, eps).view(B, Fr, C, h * w)
     if layout == 0:                                                     # (b f) (h w) c
@@ -134,6 +150,7 @@ def groupnorm_tokens(x, gamma, beta, groups=32, eps=1e-6, layout=0):
 
 
 def _ln(x, gamma, beta, eps, pe, seq_len):
+    _strict(x.shape[-1] in (64, 320, 640, 1280), f"LayerNorm width {x.shape[-1]} (64, 320, 640, 1280)")
     n = F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps)
     if pe is not None:
         n = (n.view(-1, seq_len, x.shape[-1]) + pe[:seq_len]).view(x.shape)
@@ -155,6 +172,7 @@ def residual_layernorm_(x, y, bias, scale, gamma, beta, eps=1e-5, pe=None, seq_l
 
 
 def geglu(hg):
+    _strict((hg.shape[-1] // 2) % 8 == 0, f"GEGLU inner width {hg.shape[-1] // 2} (multiple of 8)")
     h, g = hg.float().chunk(2, dim=-1)
     return (h * F.gelu(g)).to(BF).contiguous()
 
@@ -178,6 +196,7 @@ def tokens_to_video(tok, bias, residual, layout=0):
 def temporal_attn(q, k, v, heads):
     T, Fr, C = q.shape
     d = C // heads
+    _strict(Fr <= 32 and d % 2 == 0 and C % 8 == 0, f"temporal attention F={Fr} head_dim={d} C={C}")
 
     def hd(t):
         return t.float().view(T, Fr, heads, d).transpose(1, 2)
@@ -218,12 +237,16 @@ EMULATED = ["epi_row_params", "epi_bias_dense", "epi_attn_fwd", "epi_attn_fwd_sh
             "pairwise_fundamental", "plucker_embedding"]
 
 
-def install(monkeypatch):
+def install(monkeypatch, strict_shapes=False):
     """Replace the C-ABI wrappers of ``cvd_b200.ops`` by the emulations above for the duration of one test.  Also gives
     the CPU ``torch.mm`` the ``out_dtype`` keyword the product uses on CUDA (bf16 operands, fp32 result straight out of the
     GEMM): on the CPU it is emulated as an fp32 product of the bf16-rounded operands."""
     from cvd_b200 import ops
     g = globals()
+    if hasattr(monkeypatch, "setitem"):
+        monkeypatch.setitem(STRICT, "on", bool(strict_shapes))          # restored when the test ends
+    else:
+        STRICT["on"] = bool(strict_shapes)
 
     def counted(fn):
         def call(*a, **k):

@@ -144,7 +144,7 @@ def test_pose_encoder_inference_host_logic_vs_reference_fixture(monkeypatch, cas
     """The INFERENCE path of CameraPoseEncoder (forward_stream of the temporal blocks, token layouts) -- its public
     forward refuses CPU tensors, so the layer sequence is driven through ``_run`` with the inference block function."""
     import cvd_b200
-    emulated_ops.install(monkeypatch)
+    emulated_ops.install(monkeypatch, strict_shapes=bool(case.get("device")))
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pose_encoder.npz"))
     n = case["name"]
     m = cvd_b200.CameraPoseEncoder(**case["kwargs"]).eval()
@@ -457,7 +457,7 @@ def test_unet_device_shape_fixture_vs_reference(golden, monkeypatch):
     so a failure of tests/test_gpu_zz_round2_late.py on the B200 points at the kernels, not at the host code or the fixture."""
     from cvd_b200 import sampler
     from cvd_b200.unet import UNet3DConditionModelPoseCond
-    emulated_ops.install(monkeypatch)
+    emulated_ops.install(monkeypatch, strict_shapes=True)       # every kernel call must be one the device accepts
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_gpu.npz"))
     m = UNet3DConditionModelPoseCond(**gi.UNET_GPU_KWARGS, amp=False)
     m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
