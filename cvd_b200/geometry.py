@@ -83,6 +83,34 @@ def folded_pose_pair(pose_file_0, pose_file_1, sample_n_frames=16, sample_size=2
     return torch.cat([Fm, Fm.permute(0, 2, 1)], dim=0).contiguous(), c2w, K
 
 
+def folded_pose_conditioning(pose_file_0, pose_file_1, sample_n_frames=16, sample_size=256):
+    """Everything ``ValRealEstate10KPoseFolded.get_batch`` derives from the two pose files (dataset_validation.py:180-271):
+    ``F_mats`` float32 [2n,3,3]; the FOLDED camera list (frame i of video 0 = camera n-1-i, of video 1 = camera n-1+i,
+    :262-268) as ``c2w`` float32 [2n,4,4], ``K`` [2n,3,3] and ``intrinsics`` float32 [2n,4] = (fx, fy, cx, cy) in pixels of
+    the ``sample_size`` image -- the input of the Pluecker embedding (``ops.plucker_embedding``), which the pipeline
+    then reshapes to ``[2, 6, n, H, W]`` (inference_epi.py:252-254).  Quirks kept: H, W = 1280, 720 swapped; trajectory 1
+    reversed and made relative to ITS first (reversed) camera; K of trajectory 0 for both, but the intrinsics of
+    trajectory 1 for the second half (:236-238)."""
+    cams0 = read_pose_file(pose_file_0)
+    cams1 = read_pose_file(pose_file_1)[::-1]
+    H, W = 1280, 720
+    crop = min(H, W)
+    rescale = sample_size / crop
+    dH, dW = (H - crop) / 2, (W - crop) / 2
+
+    def intr(c):
+        return [W * rescale * c.fx, H * rescale * c.fy, (W * c.cx - dW) * rescale, (H * c.cy - dH) * rescale]
+    i0 = np.array([intr(c) for c in cams0])
+    i1 = np.array([intr(c) for c in cams1])
+    Fm, c2w, K = folded_pose_pair(pose_file_0, pose_file_1, sample_n_frames, sample_size)
+    intrinsics = np.concatenate([i0[1:][::-1], i1], axis=0)
+    n = sample_n_frames
+    fold = np.concatenate([n - 1 - np.arange(n), n - 1 + np.arange(n)])
+    return dict(F_mats=Fm, c2w=torch.from_numpy(np.ascontiguousarray(c2w[fold])).float(),
+                K=np.ascontiguousarray(K[fold]), intrinsics=torch.from_numpy(np.ascontiguousarray(intrinsics[fold])).float(),
+                fold_indices=fold, c2w_all=c2w, intrinsics_all=intrinsics)
+
+
 def pairwise_fundamental_matrices(c2w, K, video_id, n_frames=16):
     """Per-UNet-call F for a view pairing (pipeline_animation_epi_advanced.py:636-647):
     row (v, f) gets F of source (v, f) -> target (video_id[v], f).  c2w [V*n,4,4], K [V*n,3,3]."""

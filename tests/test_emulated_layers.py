@@ -477,3 +477,38 @@ def test_unet_device_shape_fixture_vs_reference(golden, monkeypatch):
         final = sampler.sample_pair(m, lat.clone(), F2, t(g["ddim_text"]), sampler.DDIMSchedule(), 4, 4.0,
                                     pose_embedding_features=poses)
     assert rel_l2(final, t(g["ddim_final"])) < 5e-2, rel_l2(final, t(g["ddim_final"]))
+
+
+def test_pair_pipeline_from_pose_files_to_latents(monkeypatch):
+    """cvd_b200.PairPipeline: pose files -> F matrices + folded Pluecker rays -> pose encoder -> UNet -> DDIM, end to end on
+    the CPU with emulated kernels (reduced-width UNet; a pose encoder whose feature widths match it).  The composition is
+    checked against the same stages called by hand (each of which is pinned to a reference fixture elsewhere)."""
+    import cvd_b200
+    from cvd_b200 import geometry, ops, sampler
+    ref = "/root/reference"
+    if not os.path.exists(ref):
+        pytest.skip("the pose files live in the reference checkout (absent on the GPU box)")
+    emulated_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))     # the pose encoder refuses CPU tensors
+    unet = _product_unet()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in unet.state_dict().items() if not k.endswith(skip)}
+    unet.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    enc = cvd_b200.CameraPoseEncoder(downscale_factor=8, channels=[32, 64], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False,
+                                     temporal_attention_nhead=8, attention_block_types=["Temporal_Self"],
+                                     temporal_position_encoding=True, temporal_position_encoding_max_len=16).eval()
+    p0, p1 = os.path.join(ref, gi.POSE_FILE_0), os.path.join(ref, gi.POSE_FILE_1)
+    pipe = cvd_b200.PairPipeline(unet, enc)
+    text = torch.randn(2, 7, 48, generator=torch.Generator().manual_seed(1)) * 0.5
+    lat = torch.randn(2, 4, 16, 8, 8, generator=torch.Generator().manual_seed(2))
+    out = pipe(text, p0, p1, height=64, width=64, num_inference_steps=3, guidance_scale=4.0, latents=lat.clone())
+    assert out.shape == lat.shape and torch.isfinite(out).all()
+    # by hand
+    cond = geometry.folded_pose_conditioning(p0, p1)
+    pl = ops.plucker_embedding(cond["intrinsics"], cond["c2w"].contiguous(), 64, 64).view(2, 16, 6, 64, 64).permute(0, 2, 1, 3, 4)
+    with torch.no_grad():
+        feats = [f.view(2, 16, f.shape[1], f.shape[2], f.shape[3]).permute(0, 2, 1, 3, 4) for f in enc(pl.contiguous())]
+        ref_out = sampler.sample_pair(unet, lat.clone(), cond["F_mats"].view(2, 16, 3, 3), text, sampler.DDIMSchedule(), 3, 4.0,
+                                      pose_embedding_features=feats)
+    assert [tuple(f.shape) for f in feats] == [(2, 32, 16, 8, 8), (2, 64, 16, 4, 4)]
+    assert torch.equal(out, ref_out)

@@ -180,3 +180,29 @@ def test_pose_encoder_matches_reference_fixture():
             assert f.shape == ref.shape
             err = float((f.double() - ref.double()).norm() / ref.double().norm())
             assert err < 2e-2, (n, i, err)
+
+
+def test_folded_pose_conditioning_matches_reference_dataset(golden, monkeypatch):
+    """geometry.folded_pose_conditioning (pose files -> F matrices, folded cameras, intrinsics) against what the REFERENCE
+    dataset derived from the shipped pose pair (tests/golden/plucker.npz: load_cameras_specific's c2w / intrinsics;
+    geometry.npz: F_mats and the checksums of the folded Pluecker embedding the pipeline consumes), with the Pluecker
+    kernel replaced by its test double."""
+    import os
+    import numpy as np
+    import torch
+    import emulated_ops
+    import golden_inputs as gi
+    from cvd_b200 import geometry, ops
+    emulated_ops.install(monkeypatch)
+    ref = "/root/reference" if os.path.exists("/root/reference") else None
+    if ref is None:
+        import pytest
+        pytest.skip("the pose files live in the reference checkout (absent on the GPU box)")
+    cond = geometry.folded_pose_conditioning(os.path.join(ref, gi.POSE_FILE_0), os.path.join(ref, gi.POSE_FILE_1))
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "plucker.npz"))
+    assert np.allclose(cond["c2w_all"], g["c2w"], atol=1e-6) and np.allclose(cond["intrinsics_all"], g["intrinsics"], rtol=1e-6)
+    assert torch.allclose(cond["F_mats"], torch.from_numpy(golden["geometry"]["F_mats"]), rtol=1e-5, atol=1e-9)
+    assert np.allclose(cond["c2w"].numpy()[None], golden["geometry"]["c2w"], atol=1e-6)
+    pl = ops.plucker_embedding(cond["intrinsics"], cond["c2w"], 256, 256).double()          # [32, 6, 256, 256], folded
+    assert abs(float(pl.sum()) / float(golden["geometry"]["plucker_sum"]) - 1) < 1e-5
+    assert abs(float(pl.abs().sum()) / float(golden["geometry"]["plucker_abs_sum"]) - 1) < 1e-6
