@@ -23,7 +23,8 @@ _ATTN_SMALL = {(160, 4), (80, 4), (40, 4)}
 
 def _strict(cond, what):
     if STRICT["on"] and not cond:
-        raise AssertionError(f"the device kernel would refuse this call: {what}")
+        from cvd_b200._lib import CvdError            # what the real wrapper raises for a refused call
+        raise CvdError(f"the device kernel would refuse this call: {what}")
 
 
 def _pixel_centres(feat, S):
@@ -88,19 +89,33 @@ def _attend(q, k_all, vt_all, rowp, partner, heads, F_mat_size):
         vs.append(vt_all.float()[idx][:, :, :d].transpose(-1, -2))                       # [R,H,N,d]
     pr = torch.softmax(torch.cat(ss, dim=-1), dim=-1)
     o = torch.matmul(pr, torch.cat(vs, dim=-2))
-    return o.transpose(1, 2).reshape(R, N, C).to(BF).contiguous()
+    return o.transpose(1, 2).reshape(R, N, C).contiguous()                 # fp32; the tensor-core kernels write bf16
 
 
 def epi_attn_fwd(q, k, vt, rowp, partner, heads, F_mat_size, dbg_s=None):
+    _strict((q.shape[2] // heads, int(round(q.shape[1] ** 0.5))) in _ATTN_TC | _ATTN_SMALL,
+            f"epi attention (head_dim={q.shape[2] // heads}, feat={int(round(q.shape[1] ** 0.5))})")
     assert q.dtype == BF and k.dtype == BF and vt.dtype == BF and partner.dtype == torch.int32
     assert vt.shape == (k.shape[0], heads, dv_rows(q.shape[2] // heads), q.shape[1])
     assert bool((vt[:, :, q.shape[2] // heads] == 1).all()), "row d of every head of v^T must be ones"
-    return _attend(q, k, vt, rowp, partner, heads, F_mat_size)
+    return _attend(q, k, vt, rowp, partner, heads, F_mat_size).to(BF)
+
+
+def epi_attn_fwd_simt(q, k, vt, rowp, partner, heads, F_mat_size, out_dtype=torch.float32):
+    STRICT_was, STRICT["on"] = STRICT["on"], False          # the CUDA-core cross-check kernel takes any (head_dim, feat)
+    try:
+        return _attend(q, k, vt, rowp, partner, heads, F_mat_size).to(out_dtype)
+    finally:
+        STRICT["on"] = STRICT_was
+
+
+def peer_gather_rows(src_ptrs, partner, dst, rows_per_src):
+    raise NotImplementedError("peer pulls need two GPUs: not part of the emulation")
 
 
 def epi_attn_fwd_sharded(q, k_srcs, vt_srcs, rows_per_src, rowp, partner, heads, F_mat_size):
     assert all(t.shape[0] == rows_per_src for t in k_srcs)
-    return _attend(q, torch.cat(list(k_srcs)), torch.cat(list(vt_srcs)), rowp, partner, heads, F_mat_size)
+    return _attend(q, torch.cat(list(k_srcs)), torch.cat(list(vt_srcs)), rowp, partner, heads, F_mat_size).to(BF)
 
 
 def _logits_and_values(q, k_all, v_all, rowp, partner, heads, F_mat_size):
@@ -232,7 +247,8 @@ def plucker_embedding(intrinsics, c2w, H, W, flip_flag=None, channel_major=True)
     return out.permute(0, 3, 1, 2).contiguous() if channel_major else out
 
 
-EMULATED = ["epi_row_params", "epi_bias_dense", "epi_attn_fwd", "epi_attn_fwd_sharded", "epi_attn_fwd_lse", "epi_attn_bwd", "groupnorm_tokens", "layernorm",
+EMULATED = ["epi_row_params", "epi_bias_dense", "epi_attn_fwd", "epi_attn_fwd_sharded", "epi_attn_fwd_lse", "epi_attn_bwd",
+            "epi_attn_fwd_simt", "peer_gather_rows", "groupnorm_tokens", "layernorm",
             "residual_layernorm_", "geglu", "residual_add_", "tokens_to_video", "temporal_attn", "add_pose_tokens", "scale_add",
             "pairwise_fundamental", "plucker_embedding"]
 

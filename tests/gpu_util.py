@@ -1,4 +1,6 @@
 """Helpers shared by the -m gpu tests."""
+import os
+
 import numpy as np
 import torch
 
@@ -7,6 +9,20 @@ import golden_inputs as gi  # noqa: F401
 
 def t(a):
     return torch.from_numpy(np.asarray(a))
+
+
+def test_device():
+    """``cuda:0`` on the B200 box.  With CVD_TEST_EMULATE=1 in the environment (build box, no GPU) the -m gpu tests run on
+    the CPU instead, tests/conftest.py having replaced the C-ABI kernels by the plain-torch test double of
+    tests/emulated_ops.py in strict device-shape mode: a dry run of the test code and of the host logic it drives, never
+    a parity claim."""
+    if os.environ.get("CVD_TEST_EMULATE") == "1":
+        return torch.device("cpu")
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda:0")
+
+
+test_device.__test__ = False
 
 
 def make_vt(v, heads):

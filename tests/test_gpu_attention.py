@@ -20,8 +20,8 @@ REL_SIMT = 2e-3    # CUDA-core fp32 kernel vs fp32 restatement (output stored as
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available(), "these tests need the B200"
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 def make_case(dev, R, feat, heads, d, seed, golden, kp=1, pair=None, qk_gain=1.0, theta=None, S=256, use_bias=True):

@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available(), "these tests need the B200"
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 def dense(Fm, feat, S, dev, theta=None):

@@ -13,8 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 def test_plucker_embedding_vs_reference(dev):

@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available(), "these tests need the B200"
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 @pytest.mark.parametrize("B,C,Fr,hw,dtype", [(2, 320, 16, 32, torch.float32), (2, 640, 16, 16, torch.float32),

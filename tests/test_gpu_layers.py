@@ -18,8 +18,8 @@ REL = 2e-2
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available(), "these tests need the B200"
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 def build_attn(C, dev, sd, **kw):

@@ -20,8 +20,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 def build(C, dev, sd, **kw):

@@ -21,8 +21,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def dev():
-    assert torch.cuda.is_available(), "these tests need the B200"
-    return torch.device("cuda:0")
+    from gpu_util import test_device
+    return test_device()
 
 
 @pytest.mark.parametrize("R,feat,d,n_src,kp", [(32, 32, 40, 1, 1), (32, 32, 40, 2, 1), (32, 16, 80, 2, 1), (32, 16, 40, 4, 2),
@@ -179,3 +179,23 @@ def test_fixed_seed_ddim_final_latents_vs_reference_unet_on_device(golden, dev):
         final = sampler.sample_pair(m, lat.to(dev), F2, torch.from_numpy(g["ddim_text"]).to(dev), sampler.DDIMSchedule(device=dev),
                                     4, 4.0, pose_embedding_features=[p.to(dev) for p in poses])
     assert_close(final, torch.from_numpy(g["ddim_final"]), rel=5e-2, what="ddim final latents")
+
+
+def test_multiview_ddim_final_latents_vs_reference_unet_on_device(dev):
+    """The V-view loop end to end on the B200 (sampler.sample_multiview + the product UNet: per-call pairing, device F
+    recompute, kv_index gather, injected re-noise; 4 views, 3 DDIM steps, multistep 2) against the oracle loop driving the
+    REFERENCE UNet at widths 320 / 640 (fixture ``mv_final`` of unet_gpu.npz).  Tolerance 5e-2; the reduced-width twin of
+    this test runs with emulated kernels on the CPU (3.4e-3)."""
+    import os
+    from cvd_b200 import sampler
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_gpu.npz"))
+    m = _fixture_unet(dev, False)
+    lat4, text4, poses4, noises = gi.unet_multiview_inputs(seed=gi.UNET_GPU_SEED + 50, channels=(320, 640), text_dim=64)
+    c2w, K = sampler.multiview_cameras(4, 16, "circle", 0.5, 256)
+    it = iter(noises)
+    np.random.seed(2024)
+    with torch.no_grad():
+        final = sampler.sample_multiview(m, lat4.to(dev), text4.to(dev), sampler.DDIMSchedule(device=dev), 3, 4.0, aux_c2w=c2w,
+                                         aux_K_mats=K, pose_embedding_features=[p.to(dev) for p in poses4], multistep=2,
+                                         noise_fn=lambda shape: next(it).to(dev))
+    assert_close(final, torch.from_numpy(g["mv_final"]), rel=5e-2, what="multiview ddim final latents")
