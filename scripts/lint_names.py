@@ -54,7 +54,11 @@ def check(path):
             for child in ast.iter_child_nodes(n):
                 if isinstance(child, (ast.FunctionDef, ast.AsyncFunctionDef, ast.Lambda)):
                     for d in getattr(child, "decorator_list", []):
+                        # comprehension targets inside a decorator expression are bound there
+                        local = {n.id for n in ast.walk(d) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Store)}
+                        scope.append(local)
                         visit(d)
+                        scope.pop()
                     for dflt in child.args.defaults + [d for d in child.args.kw_defaults if d is not None]:
                         visit(ast.Expr(value=dflt))
                     walk(child, scope)
