@@ -683,21 +683,25 @@ def run_ours(args):
             cap = torch.cuda.Stream()
             cap.wait_stream(torch.cuda.current_stream())
             g_ = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_, stream=cap):
+            # thread_local: the process group's watchdog thread polls CUDA events while we capture; only THIS thread's calls
+            # are part of (and may invalidate) the capture
+            with torch.cuda.graph(g_, stream=cap, capture_error_mode="thread_local"):
                 value_step(False)
             launches_per_step = ops.LAUNCHES - l0
-            for _ in range(2):
-                g_.replay()
             graph = g_
         except Exception as exc:      # capture is an optimisation: fall back to the eager loop, and say so
             print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed ({type(exc).__name__}: {exc}); "
                   f"timing the eager loop", file=sys.stderr, flush=True)
             graph = None
-        # every rank must take the same path (a graph replay and an eager step issue the same barriers, but keep it simple)
+        # Every rank must take the same path, and must agree on it BEFORE the first replay: a replay executes the step's
+        # cross-rank barriers, which a rank whose capture failed would never answer (capturing executes nothing).
         flag = torch.tensor([1 if graph is not None else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             graph = None
+        if graph is not None:
+            for _ in range(2):
+                graph.replay()
         barrier()
     clocks = ClockSampler(local)
     clocks.start()

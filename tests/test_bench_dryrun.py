@@ -44,13 +44,22 @@ class _Event:
 
 
 class _Graph:
+    replays = 0
+    modes = []
+
     def replay(self):
-        pass
+        _Graph.replays += 1
+
+
+CAPTURE_FAILS = False        # the stand-in capture raises at its end, as an invalidated capture does
 
 
 @contextlib.contextmanager
-def _graph_ctx(graph, stream=None):
+def _graph_ctx(graph, stream=None, capture_error_mode="global"):
+    _Graph.modes.append(capture_error_mode)
     yield
+    if CAPTURE_FAILS:
+        raise RuntimeError("CUDA error: operation failed due to a previous error during capture")
 
 
 def fake_cuda(monkeypatch):
@@ -125,7 +134,7 @@ def test_bench_reference_arm_honours_warmup(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
-@pytest.mark.parametrize("no_graph", [False, True])
+@pytest.mark.parametrize("no_graph", [False, True, "capture_fails", "peer_capture_fails"])
 def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     """The N > 1 branch of ``run_ours`` in ONE process: rank 0 of a pretended world of 2 whose "peer" buffers alias its own
     (symmetric memory, the process group and the collectives replaced by stand-ins).  Exercises the chunk / run plans of
@@ -147,7 +156,13 @@ def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     monkeypatch.setattr(dist, "get_world_size", lambda group=None: 2)
     monkeypatch.setattr(dist, "get_rank", lambda group=None: 0)
     monkeypatch.setattr(dist, "barrier", lambda *a, **k: None)
-    monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: None)
+    # "peer_capture_fails": the MIN all-reduce of the captured-flag comes back 0 although this rank's capture worked
+    scenario = no_graph
+    monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: t.zero_() if (scenario == "peer_capture_fails" and k.get("op") == dist.ReduceOp.MIN) else None)
+    monkeypatch.setattr(sys.modules[__name__], "CAPTURE_FAILS", no_graph == "capture_fails")
+    _Graph.replays, _Graph.modes = 0, []
+    failed = no_graph in ("capture_fails", "peer_capture_fails")
+    no_graph = no_graph is True or failed
     barriers = []
 
     class Handle:
@@ -184,11 +199,15 @@ def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     monkeypatch.setattr(bench, "CALLS_PER_SHAPE", 1)
     monkeypatch.setattr(bench, "cpu_reference_step", lambda R, reps, warm: ([1.0] * reps, 1e9, 1))
     args = types.SimpleNamespace(gpus=2, steps=2, warmup=1, impl="ours", no_denoise=True, no_extras=False, exchange="dma",
-                                 no_graph=no_graph)
+                                 no_graph=no_graph and not failed)
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
         bench.run_ours(args)
     d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][0])
+    # a rank never replays (= executes cross-rank barriers) unless EVERY rank captured; then 2 warm replays + the steps
+    assert _Graph.replays == (0 if no_graph else 2 + 2)
+    # captured beside a live process-group watchdog thread: only this thread's calls belong to the capture
+    assert _Graph.modes == ([] if (no_graph and not failed) else ["thread_local"])
     assert d["n_gpus"] == 2 and d["config"]["views_total"] == 4 and "copy engines" in d["config"]["parallelism"]
     assert all(t_ == sharding.BARRIER_TIMEOUT_MS for t_ in barriers) and len(barriers) > 0
     # per step: 4 prepasses + the chunk launches of 32x32 and 16x16 (graph: 3 + 3 wave-sized chunks; eager: the two-chunk
