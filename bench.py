@@ -426,23 +426,24 @@ def full_unet_bench(dev, steps):
     return out
 
 
-def extras_single_gpu(dev, peak_bw, F_rows):
-    """Two more measurements for the N = 1 line, each guarded (a failure is reported in the line, never fatal):
-
-    roofline_glue : achieved HBM GB/s of every glue kernel (GroupNorm + layout, LayerNorm, residual, GEGLU, temporal
-                    attention, ...) at the config-2 shapes against the measured copy bandwidth (scripts/profile_glue.py).
-    reference_gpu : the reference's own PyTorch GPU path (oracle/gpu_reference.py: fp32 eager -- dense bias per call, NaN
-                    check with its host sync, mask x 8 heads, SDPA -- and the same under bf16 autocast) for ONE
-                    EpiSelfAttention.forward per shape on device tensors, beside the product layer on the same inputs."""
-    glue_rows = ref_gpu = None
+def glue_extra(dev, peak_bw):
+    """roofline_glue : achieved HBM GB/s of every glue kernel (GroupNorm + layout, LayerNorm, residual, GEGLU, temporal
+    attention, ...) at the config-2 shapes against the measured copy bandwidth (scripts/profile_glue.py).  A failure is
+    reported in the line, never fatal."""
     try:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import profile_glue
         rows = profile_glue.measure(dev, peak_bw)
-        glue_rows = [{"kernel": r["kernel"], "shape": r["shape"], "us": round(r["us"], 2), "gbs": round(r["gbs"], 1),
-                      "frac": round(r["frac"], 4)} for r in rows]
+        return [{"kernel": r["kernel"], "shape": r["shape"], "us": round(r["us"], 2), "gbs": round(r["gbs"], 1),
+                 "frac": round(r["frac"], 4)} for r in rows]
     except Exception as exc:
-        glue_rows = {"error": f"{type(exc).__name__}: {exc}"}
+        return {"error": f"{type(exc).__name__}: {exc}"}
+
+
+def reference_gpu_extra(dev, F_rows):
+    """reference_gpu : the reference's own PyTorch GPU path (oracle/gpu_reference.py: fp32 eager -- dense bias per call, NaN
+    check with its host sync, mask x 8 heads, SDPA -- and the same under bf16 autocast) for ONE EpiSelfAttention.forward
+    per shape on device tensors, beside the product layer on the same inputs.  Guarded like glue_extra."""
     try:
         import cvd_b200
         import golden_inputs as gi
@@ -489,7 +490,63 @@ def extras_single_gpu(dev, peak_bw, F_rows):
                    "speedup_vs_fp32": tot["fp32"] / tot["ours"], "speedup_vs_bf16_autocast": tot["bf16_autocast"] / tot["ours"]}
     except Exception as exc:
         ref_gpu = {"error": f"{type(exc).__name__}: {exc}"}
-    return glue_rows, ref_gpu
+    return ref_gpu
+
+
+EXTRA_KEYS = ("roofline_glue", "reference_gpu", "full_unet")
+EXTRAS_TIMEOUT_S = 600
+
+
+def extras_measurements(dev, steps, denoise):
+    """The explanatory measurements of the N = 1 line, one (key, result) at a time: roofline_glue, reference_gpu and, with
+    the denoise measurement on, the whole-UNet steps/s (full_unet_bench)."""
+    _, peak_bw, _ = load_peaks()
+    yield "roofline_glue", glue_extra(dev, peak_bw)
+    yield "reference_gpu", reference_gpu_extra(dev, cfg_F_mats(1).to(dev))
+    if denoise:
+        try:
+            res = full_unet_bench(dev, max(2, min(steps, 3)))
+        except Exception as exc:
+            res = {"error": f"{type(exc).__name__}: {exc}"}
+        yield "full_unet", res
+
+
+def run_extras(args):
+    """``--impl extras``: the child process of collect_extras -- one JSON line per finished measurement."""
+    from cvd_b200 import _lib
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(0)
+    _lib.load()
+    for key, res in extras_measurements(torch.device("cuda", 0), args.steps, not args.no_denoise):
+        print(json.dumps({"extra": key, "result": res}), flush=True)
+
+
+def collect_extras(cmd, timeout_s, keys):
+    """Runs the extras in a CHILD process and returns {key: result}.  They are explanations beside the headline numbers:
+    a measurement that dies (a CUDA error is sticky for its whole process) or hangs must not take the line's value / e2e /
+    roofline with it, so the child is bounded by ``timeout_s`` and whatever it did not deliver is reported as an error."""
+    note = None
+    try:
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+        stdout = proc.stdout
+        if proc.returncode != 0:
+            note = f"extras process exited with {proc.returncode}: " + " | ".join((proc.stderr or "").strip().splitlines()[-3:])
+    except subprocess.TimeoutExpired as exc:
+        stdout = exc.stdout.decode(errors="replace") if isinstance(exc.stdout, bytes) else (exc.stdout or "")
+        note = f"extras process killed after {timeout_s} s"
+    except OSError as exc:
+        stdout, note = "", f"extras process not started: {exc}"
+    out = {}
+    for ln in stdout.splitlines():
+        if ln.startswith('{"extra"'):
+            try:
+                d = json.loads(ln)
+                out[d["extra"]] = d["result"]
+            except (ValueError, KeyError):
+                pass
+    for k in keys:
+        out.setdefault(k, {"error": note or "extras process delivered no result"})
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -814,12 +871,13 @@ def run_ours(args):
 
     glue_rows = ref_gpu = full_unet = None
     if world == 1 and not args.no_extras:
-        glue_rows, ref_gpu = extras_single_gpu(dev, peak_bw, F_rows)
-        if not args.no_denoise:
-            try:
-                full_unet = full_unet_bench(dev, max(2, min(args.steps, 3)))
-            except Exception as exc:
-                full_unet = {"error": f"{type(exc).__name__}: {exc}"}
+        keys = EXTRA_KEYS if not args.no_denoise else EXTRA_KEYS[:2]
+        if "CVD_BENCH_DRYRUN_DEVICE" in os.environ:      # the dry run's test doubles live in THIS process
+            ex = dict(extras_measurements(dev, args.steps, not args.no_denoise))
+        else:
+            ex = collect_extras([sys.executable, os.path.abspath(__file__), "--impl", "extras", "--steps", str(args.steps)]
+                                + (["--no-denoise"] if args.no_denoise else []), EXTRAS_TIMEOUT_S, keys)
+        glue_rows, ref_gpu, full_unet = ex.get("roofline_glue"), ex.get("reference_gpu"), ex.get("full_unet")
 
     # max over ranks
     if world > 1:
@@ -881,7 +939,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "extras"])
     ap.add_argument("--no-denoise", action="store_true", help="skip the UNet-level steps/s measurement")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip roofline_by_shape / roofline_glue / reference_gpu (N = 1 only; a few seconds)")
@@ -897,6 +955,8 @@ def main():
         EXCHANGE = "NVLink peer pull, cvd_peer_gather_rows"
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "extras":
+        run_extras(args)
     else:
         run_ours(args)
 

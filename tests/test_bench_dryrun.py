@@ -278,3 +278,37 @@ def test_full_unet_bench_control_flow(monkeypatch):
     out = bench.full_unet_bench(torch.device("cpu"), 2)
     assert out["steps_per_s"] == 2000.0 and out["views"] == 2 and out["parameters_M"] > 1.0
     assert out["forward"]["rel_l2"] < 2e-2, out["forward"]
+
+
+def test_extras_run_in_a_bounded_child_process(tmp_path):
+    """collect_extras: results the child printed are kept; whatever it did not deliver (crash, non-zero exit, hang past the
+    limit, nothing printed) becomes an {"error": ...} entry -- the bench line survives either way."""
+    sys.path.insert(0, ROOT)
+    import bench
+    keys = ("roofline_glue", "reference_gpu", "full_unet")
+    ok = ('import json; print("noise"); print(json.dumps({"extra": "roofline_glue", "result": [1, 2]}), flush=True); '
+          'print(json.dumps({"extra": "reference_gpu", "result": {"speedup_vs_fp32": 9.0}}), flush=True); ')
+    out = bench.collect_extras([sys.executable, "-c", ok + 'print(json.dumps({"extra": "full_unet", "result": {"steps_per_s": 3.0}}))'],
+                               30, keys)
+    assert out == {"roofline_glue": [1, 2], "reference_gpu": {"speedup_vs_fp32": 9.0}, "full_unet": {"steps_per_s": 3.0}}
+    # dies after two results (a sticky CUDA error ends in an abort): the two survive, the third says why it is missing
+    out = bench.collect_extras([sys.executable, "-c", ok + 'import os, sys; sys.stderr.write("CUDA error: boom\\n"); os._exit(134)'],
+                               30, keys)
+    assert out["roofline_glue"] == [1, 2] and "134" in out["full_unet"]["error"] and "boom" in out["full_unet"]["error"]
+    # hangs: killed at the limit, delivered results kept
+    out = bench.collect_extras([sys.executable, "-c", ok + 'import time; time.sleep(60)'], 3, keys)
+    assert out["reference_gpu"] == {"speedup_vs_fp32": 9.0} and "killed after 3 s" in out["full_unet"]["error"]
+    out = bench.collect_extras([str(tmp_path / "no_such_binary")], 3, keys)
+    assert all("not started" in out[k]["error"] for k in keys)
+
+
+def test_extras_child_refuses_to_run_without_a_gpu():
+    """The real ``bench.py --impl extras`` child on this box (no GPU): it must fail loudly (no CPU fallback), and the
+    parent-side collector turns that into error entries."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU build box only")
+    sys.path.insert(0, ROOT)
+    import bench
+    out = bench.collect_extras([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "extras", "--steps", "2"], 300,
+                               bench.EXTRA_KEYS)
+    assert all("error" in out[k] and "needs a GPU" in out[k]["error"] for k in bench.EXTRA_KEYS), out
