@@ -22,7 +22,10 @@ symmetric memory and every call reads exactly its partner rows across NVLink aft
 barrier: by the copy engines in row chunks, the smallest first, each chunk's attention running under
 the transfer of the next (--exchange dma, default; latents <= 8x8 are read inside the attention
 kernel by unicast TMA over NVLink), by our pull kernel (--exchange peer), or as an NCCL all-gather of
-every rank's rows (--exchange allgather, the baseline).  The N > 1 step replays as one CUDA graph.
+every rank's rows (--exchange allgather, the baseline).  At N > 1 the step is timed twice: issued eagerly
+(two-chunk plan, phase A) and -- last, with every other number of the line already safe -- replayed as ONE CUDA
+graph (wave-sized chunks, phase B); the replay becomes the line's value only if every rank captured it, its
+outputs equal the eager step's bit for bit and it is faster (config.exchange_issue says which).
 """
 import argparse
 import json
@@ -46,7 +49,7 @@ HEADS = 8
 R_PER_GPU = 64                                           # 2 views x 2 cfg x 16 frames
 F_MAT_SIZE = 256
 DENOISE_FEAT, DENOISE_LEVELS = 32, 4                     # latent size / UNet levels of the denoise measurement (256x256 images)
-EXCHANGE = "NVLink copy engines in row chunks (smallest first) under the attention, K and V^T on two streams; grids <= 8x8 read the peer's K/V^T in-kernel (unicast TMA over NVLink); the whole step replays as one CUDA graph"
+EXCHANGE = "NVLink copy engines in row chunks (smallest first) under the attention, K and V^T on two streams; grids <= 8x8 read the peer's K/V^T in-kernel (unicast TMA over NVLink); issue: config.exchange_issue"
 
 
 def step_flops(R, shapes=SHAPES, calls=CALLS_PER_SHAPE):
@@ -254,40 +257,46 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
             torch.cuda.synchronize()
             ms_eager = e2.elapsed_time(e3) / steps
     assert torch.isfinite(out).all()
-    by_views = None
+    by_views = config4 = None
     if world > 1 and 24 % world == 0:
-        # BASELINE config 4: 6-view 'upper_hemi' generation, accumulate_step 2 -> 6 x 2 (cfg) x 2 (acc) = 24 independent
-        # UNet evaluations per update, sharded as UNITS (24 / world per GPU: 3 on 8 GPUs), partner rows through the layers'
-        # NVLink exchange, one small all-reduce of the weighted predictions per update (sampler.sample_multiview_units).
-        # Guarded: a failure is reported in the line (every rank runs the same host logic, so it fails on all or none).
-        try:
-            V6 = 6
-            g6 = torch.Generator(device=dev).manual_seed(43)
-            lat6 = torch.randn(V6, 4, 16, ft, ft, device=dev, generator=g6)
-            poses6 = [torch.randn(V6, c, 16, ft >> i, ft >> i, device=dev, generator=g6) for i, c in enumerate(chans)]
-            text6 = torch.randn(2, 77, 768, device=dev, generator=g6).repeat(V6, 1, 1)
-            c2w6, K6 = sampler.multiview_cameras(V6, 16, "upper_hemi", 0.5, 256)
+        def config4():
+            """BASELINE config 4: 6-view 'upper_hemi' generation, accumulate_step 2 -> 6 x 2 (cfg) x 2 (acc) = 24 independent
+            UNet evaluations per update, sharded as UNITS (24 / world per GPU: 3 on 8 GPUs), partner rows through the layers'
+            NVLink exchange, one small all-reduce of the weighted predictions per update (sampler.sample_multiview_units).
+            Returned to the caller, which runs it LAST (its code had not run on hardware when this was written).  A Python
+            exception is reported in the line (every rank runs the same host logic, so it fails on all ranks or none)."""
+            try:
+                V6 = 6
+                g6 = torch.Generator(device=dev).manual_seed(43)
+                lat6 = torch.randn(V6, 4, 16, ft, ft, device=dev, generator=g6)
+                poses6 = [torch.randn(V6, c, 16, ft >> i, ft >> i, device=dev, generator=g6) for i, c in enumerate(chans)]
+                text6 = torch.randn(2, 77, 768, device=dev, generator=g6).repeat(V6, 1, 1)
+                c2w6, K6 = sampler.multiview_cameras(V6, 16, "upper_hemi", 0.5, 256)
 
-            def run6(n):
-                return sampler.sample_multiview_units(net, lat6, text6, sch, n, 8.5, aux_c2w=c2w6, aux_K_mats=K6,
-                                                      pose_embedding_features=poses6, accumulate_step=2, shard=shard)
-            with torch.no_grad():
-                run6(2)
-                torch.distributed.barrier()
-                torch.cuda.synchronize()
-                a6, b6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a6.record()
-                o6 = run6(steps)
-                b6.record()
-                torch.distributed.barrier()
-                torch.cuda.synchronize()
-            ms6 = torch.tensor([a6.elapsed_time(b6) / steps], device=dev, dtype=torch.float64)
-            torch.distributed.all_reduce(ms6, op=torch.distributed.ReduceOp.MAX)
-            by_views = {"config4": {"steps_per_s": 1e3 / float(ms6.item()), "views": V6, "accumulate_step": 2,
+                def run6(n):
+                    return sampler.sample_multiview_units(net, lat6, text6, sch, n, 8.5, aux_c2w=c2w6, aux_K_mats=K6,
+                                                          pose_embedding_features=poses6, accumulate_step=2, shard=shard)
+                with torch.no_grad():
+                    run6(2)
+                    torch.distributed.barrier()
+                    torch.cuda.synchronize()
+                    a6, b6 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a6.record()
+                    o6 = run6(steps)
+                    b6.record()
+                    torch.distributed.barrier()
+                    torch.cuda.synchronize()
+                ms6 = torch.tensor([a6.elapsed_time(b6) / steps], device=dev, dtype=torch.float64)
+                torch.distributed.all_reduce(ms6, op=torch.distributed.ReduceOp.MAX)
+                return {"config4": {"steps_per_s": 1e3 / float(ms6.item()), "views": V6, "accumulate_step": 2,
                                     "units_per_gpu": 24 // world, "rig": "upper_hemi", "finite": bool(torch.isfinite(o6).all()),
                                     "loop": "sampler.sample_multiview_units ((view, cfg, acc) units sharded, one all-reduce per update)"}}
-        except Exception as exc:
-            by_views = {"config4": {"error": f"{type(exc).__name__}: {exc}"}}
+            except RuntimeError as exc:
+                if "CUDA" in str(exc):      # not survivable here: the caller prints the held line and leaves
+                    raise
+                return {"config4": {"error": f"{type(exc).__name__}: {exc}"}}
+            except Exception as exc:
+                return {"config4": {"error": f"{type(exc).__name__}: {exc}"}}
     if world == 1:
         # BASELINE metric "denoise steps/s at 2/4/6 views": the V-view loop (fresh pairing, device F recompute and kv_index
         # gather per UNet call) with all V views on this one GPU (R = 32 V rows), multistep = 1
@@ -312,7 +321,7 @@ def denoise_bench(dev, world, rank, shard, peer, steps):
             assert torch.isfinite(o).all()
             by_views[str(Vn)] = {"steps_per_s": 1e3 / (a.elapsed_time(b) / steps), "rows": 32 * Vn,
                                  "launch": "one CUDA graph per UNet forward (kv_index on the device)", "rig": rig}
-    return e0.elapsed_time(e1) / steps, V, ms_eager, by_views
+    return e0.elapsed_time(e1) / steps, V, ms_eager, by_views, config4
 
 
 # SD-1.5 + AnimateDiff v3 + CameraCtrl + CVD: the UNet of configs/inference_config.yaml (unet_additional_kwargs) on top of the
@@ -495,6 +504,12 @@ def reference_gpu_extra(dev, F_rows):
 
 EXTRA_KEYS = ("roofline_glue", "reference_gpu", "full_unet")
 EXTRAS_TIMEOUT_S = 600
+LATE_TIMEOUT_S = 300         # N > 1: graph replay + config-4 measurement together (seconds of GPU work when healthy)
+
+
+def hard_exit(code):
+    """Leave without running any CUDA / process-group teardown (used after a CUDA error or a hang in a late measurement)."""
+    os._exit(code)
 
 
 def extras_measurements(dev, steps, denoise):
@@ -663,17 +678,21 @@ def run_ours(args):
         run_plan_eager = {f: [runs_of(lo, hi) for lo, hi in ch] for f, ch in chunk_plan_eager.items()}
         runs_whole = runs_of(0, R)
 
+    keep = {"outs": None}      # a list here collects every attention output of a step (graph replay vs eager check)
+
     def timed_attn(record, *a):
         """One attention launch; with ``record`` its CUDA-event pair joins the event list of the current call (a call of
         the dominant shape is one launch, or one launch per row chunk: the chunk times add up to the call)."""
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.epi_attn_fwd(*a)
+            o = ops.epi_attn_fwd(*a)
             e1.record()
             big_events[-1].append((e0, e1))
         else:
-            ops.epi_attn_fwd(*a)
+            o = ops.epi_attn_fwd(*a)
+        if keep["outs"] is not None:
+            keep["outs"].append(o)
 
     def value_step(record, eager_plan=False):
         chunks_of, runs_for = (chunk_plan_eager, run_plan_eager) if eager_plan else (chunk_plan, run_plan)
@@ -696,7 +715,7 @@ def run_ours(args):
                         # out of the peer's HBM (unicast TMA over NVLink, plain loads at 4x4) -- every byte crosses once,
                         # no landing buffer, no copy launch
                         src = runs_whole[0][2]
-                        ops.epi_attn_fwd(q, xk[2][src], xv[2][src], rowp, partner_local, HEADS, F_MAT_SIZE)
+                        timed_attn(False, q, xk[2][src], xv[2][src], rowp, partner_local, HEADS, F_MAT_SIZE)
                         continue
                     # ... then the partner rows cross NVLink on the COPY ENGINES in row chunks (K and V^T on two side
                     # streams), each chunk's attention running under the transfer of the next (no SMs spent on the pull)
@@ -726,61 +745,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Phase A: the step issued EAGERLY -- at N > 1 with the two-chunk plan of round 1, the path that has run on hardware.
+    # (The CUDA-graph replay of the N > 1 step is measured in phase B, after every other number of the line is safe.)
     for _ in range(max(args.warmup, 3)):
-        value_step(False)
+        value_step(False, eager_plan=True)
     barrier()
-    # N > 1: the step is ~15 stream operations per call (barrier, event hand-offs, peer copies, chunk launches): issued
-    # eagerly the host cannot keep up with the GPU (round 1: SMs idle, 385 W).  The whole step is captured ONCE into a CUDA
-    # graph (device-side barriers, copy-engine transfers and kernels alike) and replayed; --no-graph times the eager loop.
-    graph = None
-    launches_per_step = None
-    if world > 1 and not args.no_graph:
-        l0 = ops.LAUNCHES
-        try:
-            cap = torch.cuda.Stream()
-            cap.wait_stream(torch.cuda.current_stream())
-            g_ = torch.cuda.CUDAGraph()
-            # thread_local: the process group's watchdog thread polls CUDA events while we capture; only THIS thread's calls
-            # are part of (and may invalidate) the capture
-            with torch.cuda.graph(g_, stream=cap, capture_error_mode="thread_local"):
-                value_step(False)
-            launches_per_step = ops.LAUNCHES - l0
-            graph = g_
-        except Exception as exc:      # capture is an optimisation: fall back to the eager loop, and say so
-            print(f"[bench] rank {rank}: CUDA-graph capture of the sharded step failed ({type(exc).__name__}: {exc}); "
-                  f"timing the eager loop", file=sys.stderr, flush=True)
-            graph = None
-        # Every rank must take the same path, and must agree on it BEFORE the first replay: a replay executes the step's
-        # cross-rank barriers, which a rank whose capture failed would never answer (capturing executes nothing).
-        flag = torch.tensor([1 if graph is not None else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
-            graph = None
-        if graph is not None:
-            for _ in range(2):
-                graph.replay()
-        barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches0 = ops.LAUNCHES
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            value_step(True, eager_plan=True)
-    t1.record()
-    barrier()
-    launches = ops.LAUNCHES - launches0 if graph is None else launches_per_step * args.steps
-    ms_value = t0.elapsed_time(t1) / args.steps
-    clk = clocks.stop()
-    if graph is not None:       # the dominant kernel's launch time: two eager passes of the same step (events per launch)
-        for _ in range(2):
-            value_step(True)
+
+    def time_steps(step_fn):
+        """EXACTLY args.steps steps between two events, barrier + synchronize on both sides, clocks sampled meanwhile."""
+        clocks = ClockSampler(local)
+        clocks.start()
+        t0.record()
+        for _ in range(args.steps):
+            step_fn()
+        t1.record()
         barrier()
-    exchange_issue = ("one CUDA graph per step" if graph is not None else "eager") if world > 1 else None
-    big_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in call) for call in big_events if call]))   # per call of R rows
+        return t0.elapsed_time(t1) / args.steps, clocks.stop()
+
+    def call_ms():      # the dominant kernel per call of R rows (a call is one launch, or one per row chunk: they add up)
+        return float(np.mean([sum(a.elapsed_time(b) for a, b in call) for call in big_events if call]))
+
+    launches0 = ops.LAUNCHES
+    ms_value, clk = time_steps(lambda: value_step(True, eager_plan=True))
+    launches = ops.LAUNCHES - launches0
+    big_ms = call_ms()
+    exchange_issue = "eager" if world > 1 else None
 
     # every attention shape on its own (N = 1): the 10 calls of the shape back to back on their distinct buffers
     by_shape = None
@@ -864,10 +854,13 @@ def run_ours(args):
     barrier()
     ms_e2e = t0.elapsed_time(t1) / e_steps
 
-    # release the kernel-bench buffers before the UNet-level measurement
-    del bufs, land, layers, hosts, dev_in
+    # release what the later measurements do not need (phase B at N > 1 replays the kernel step: its buffers stay)
+    del layers, hosts, dev_in
+    if world == 1:
+        del bufs, land
     torch.cuda.empty_cache()
-    ms_denoise, views, ms_eager, by_views = (None, 0, None, None) if args.no_denoise else denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
+    ms_denoise, views, ms_eager, by_views, config4 = (None, 0, None, None, None) if args.no_denoise else \
+        denoise_bench(dev, world, rank, shard, peer, max(3, min(args.steps, 5)))
 
     glue_rows = ref_gpu = full_unet = None
     if world == 1 and not args.no_extras:
@@ -889,6 +882,7 @@ def run_ours(args):
     big_flops = 4.0 * R * 1024 * 1024 * 320
     achieved = big_flops / (big_ms * 1e-3) / 1e12
 
+    line = None
     if rank == 0:
         cb_times, cb_flops, cores = cpu_reference_step(R, reps=2, warm=1)
         cb_val = cb_flops / min(cb_times) / 1e12
@@ -929,9 +923,126 @@ def run_ours(args):
                 line["denoise"]["by_views"] = by_views
             if full_unet is not None:
                 line["denoise"]["full_unet"] = full_unet
+    if world == 1:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return
+
+    # Phase B (N > 1): two measurements whose code had not run on hardware when this was written -- the step replayed as ONE
+    # CUDA graph, and the unit-sharded config-4 loop.  Rank 0 HOLDS the finished line (phase A numbers) meanwhile; each
+    # result is merged into it in one piece; an exception (a CUDA error is sticky for the process) or LATE_TIMEOUT_S without
+    # an end prints the line as it stands and leaves the process without touching CUDA again.
+    lock = threading.Lock()
+    done = [False]
+
+    def emit(note=None, hard=False):
+        with lock:
+            if done[0]:
+                return
+            done[0] = True
+            if rank == 0:
+                if note:
+                    line["config"]["late_measurements"] = note
+                print(json.dumps(line), flush=True)
+        if hard:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            hard_exit(0)
+
+    def merge(fn):
+        with lock:
+            if rank == 0 and not done[0]:
+                fn(line)
+
+    timer = threading.Timer(LATE_TIMEOUT_S, emit, kwargs=dict(
+        note=f"graph replay / config-4 measurement still running after {LATE_TIMEOUT_S} s: line printed without them", hard=True))
+    timer.daemon = True
+    timer.start()
+    try:
+        if not args.no_graph and args.exchange == "dma":
+            # The step is ~15 stream operations per call (barrier, event hand-offs, peer copies, chunk launches): issued
+            # eagerly the host cannot keep up with the GPU (round 1: SMs idle, 385 W).  Captured ONCE (device-side barriers,
+            # copy-engine transfers and kernels alike, wave-sized chunk plan) and replayed, the host is out of the loop.
+            graph, why, graph_outs, launches_per_step = None, None, None, 0
+            l0 = ops.LAUNCHES
+            try:
+                cap = torch.cuda.Stream()
+                cap.wait_stream(torch.cuda.current_stream())
+                g_ = torch.cuda.CUDAGraph()
+                keep["outs"] = []
+                # thread_local: the process group's watchdog thread polls CUDA events while we capture; only THIS thread's
+                # calls are part of (and may invalidate) the capture
+                with torch.cuda.graph(g_, stream=cap, capture_error_mode="thread_local"):
+                    value_step(False)
+                graph_outs = keep["outs"]
+                launches_per_step = ops.LAUNCHES - l0
+                graph = g_
+            except Exception as exc:      # capture is an optimisation: the eager numbers stand, and the line says why
+                why = f"capture failed on rank {rank} ({type(exc).__name__}: {exc})"
+                print(f"[bench] {why}", file=sys.stderr, flush=True)
+            keep["outs"] = None
+            # Every rank must take the same path, and must agree on it BEFORE the first replay: a replay executes the step's
+            # cross-rank barriers, which a rank whose capture failed would never answer (capturing executes nothing).
+            flag = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graph, why = None, why or "capture failed on another rank"
+            if graph is not None:
+                for _ in range(2):
+                    graph.replay()
+                barrier()
+                # the replay must give the eager step's bits (same kernels on the same rows; only chunking and issue differ)
+                keep["outs"] = []
+                value_step(False, eager_plan=True)
+                eager_outs, keep["outs"] = keep["outs"], None
+                torch.cuda.synchronize()
+
+                def by_shape_rows(outs_):      # consecutive outputs of one (N, C) -> [calls * R, N, C], rows in call order
+                    groups = []
+                    for o in outs_:
+                        if groups and groups[-1][0].shape[1:] == o.shape[1:]:
+                            groups[-1].append(o)
+                        else:
+                            groups.append([o])
+                    return [torch.cat(g) for g in groups]
+                ga, ea = by_shape_rows(graph_outs), by_shape_rows(eager_outs)
+                same = len(ga) == len(ea) and all(x.shape == y.shape and torch.equal(x, y) for x, y in zip(ga, ea))
+                del ga, ea, eager_outs
+                flag.fill_(1 if same else 0)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    graph, why = None, "the graph replay's outputs differ from the eager step's: not used"
+            if graph is not None:
+                ms_graph, clk_graph = time_steps(graph.replay)
+                big_events.clear()      # the dominant kernel's launch times under the graph's chunk plan: two eager passes
+                for _ in range(2):
+                    value_step(True)
+                barrier()
+                tg = torch.tensor([ms_graph, call_ms()], device=dev, dtype=torch.float64)
+                dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+                ms_graph, big_graph = (float(v) for v in tg.tolist())
+
+                def use_graph(ln):
+                    ln["config"]["exchange_ms_per_step"] = {"eager": ln["ms_per_step"], "graph": ms_graph,
+                                                            "graph_equals_eager_bitwise": True}
+                    if ms_graph < ln["ms_per_step"]:
+                        ach = big_flops / (big_graph * 1e-3) / 1e12
+                        ln.update(value=flops / (ms_graph * 1e-3) / 1e12, ms_per_step=ms_graph, clocks=clk_graph,
+                                  gpu_launches=launches_per_step * args.steps)
+                        ln["config"]["exchange_issue"] = "one CUDA graph per step"
+                        ln["roofline"].update(achieved=ach, frac=ach / peak_tf, ms_per_launch=big_graph)
+                merge(use_graph)
+            else:
+                merge(lambda ln: ln["config"].__setitem__("graph", why))
+        if config4 is not None:
+            res4 = config4()
+            merge(lambda ln: ln["denoise"].setdefault("by_views", {}).update(res4))
+    except Exception as exc:      # most likely a CUDA error: this process can print, and nothing else
+        timer.cancel()
+        emit(note=f"ended by {type(exc).__name__}: {str(exc).splitlines()[0] if str(exc) else ''}", hard=True)
+        return
+    timer.cancel()
+    emit()
+    dist.destroy_process_group()
 
 
 def main():
@@ -946,7 +1057,7 @@ def main():
     ap.add_argument("--exchange", default="dma", choices=["peer", "dma", "allgather"],
                     help="N>1: partner rows over NVLink by the copy engines in row chunks under the attention, small grids read "
                          "in-kernel (dma, default), by our pull kernel (peer), or NCCL all-gather (baseline)")
-    ap.add_argument("--no-graph", action="store_true", help="N>1: issue the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: skip phase B's CUDA-graph replay of the step (the eagerly issued step is timed either way)")
     args = ap.parse_args()
     global EXCHANGE
     if args.exchange == "allgather":

@@ -9,6 +9,7 @@ import io
 import json
 import os
 import sys
+import threading
 import types
 
 import pytest
@@ -39,16 +40,25 @@ class _Event:
     def wait(self, stream=None):
         pass
 
+    ms = 1.0                 # what every event pair "measures"; a stand-in graph replay makes it 0.25 (see _Graph)
+
     def elapsed_time(self, other):
-        return 1.0
+        return _Event.ms
 
 
 class _Graph:
     replays = 0
     modes = []
 
+    on_replay = None
+    replay_ms = None         # when set: after a replay every event pair "measures" this (a replayed step that is faster)
+
     def replay(self):
         _Graph.replays += 1
+        if _Graph.replay_ms is not None:
+            _Event.ms = _Graph.replay_ms
+        if _Graph.on_replay is not None:
+            _Graph.on_replay()
 
 
 CAPTURE_FAILS = False        # the stand-in capture raises at its end, as an invalidated capture does
@@ -64,6 +74,9 @@ def _graph_ctx(graph, stream=None, capture_error_mode="global"):
 
 def fake_cuda(monkeypatch):
     cur = _Stream()
+    monkeypatch.setattr(_Event, "ms", 1.0)
+    monkeypatch.setattr(_Graph, "on_replay", None)
+    monkeypatch.setattr(_Graph, "replay_ms", None)
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: cur)
@@ -134,7 +147,7 @@ def test_bench_reference_arm_honours_warmup(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
 
 
-@pytest.mark.parametrize("no_graph", [False, True, "capture_fails", "peer_capture_fails"])
+@pytest.mark.parametrize("no_graph", [False, True, "capture_fails", "peer_capture_fails", "replay_dies", "replay_hangs"])
 def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     """The N > 1 branch of ``run_ours`` in ONE process: rank 0 of a pretended world of 2 whose "peer" buffers alias its own
     (symmetric memory, the process group and the collectives replaced by stand-ins).  Exercises the chunk / run plans of
@@ -162,7 +175,8 @@ def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     monkeypatch.setattr(sys.modules[__name__], "CAPTURE_FAILS", no_graph == "capture_fails")
     _Graph.replays, _Graph.modes = 0, []
     failed = no_graph in ("capture_fails", "peer_capture_fails")
-    no_graph = no_graph is True or failed
+    late = no_graph in ("replay_dies", "replay_hangs")
+    no_graph = no_graph is True or failed or late
     barriers = []
 
     class Handle:
@@ -199,23 +213,60 @@ def test_bench_sharded_run_control_flow(monkeypatch, no_graph):
     monkeypatch.setattr(bench, "CALLS_PER_SHAPE", 1)
     monkeypatch.setattr(bench, "cpu_reference_step", lambda R, reps, warm: ([1.0] * reps, 1e9, 1))
     args = types.SimpleNamespace(gpus=2, steps=2, warmup=1, impl="ours", no_denoise=True, no_extras=False, exchange="dma",
-                                 no_graph=no_graph and not failed)
+                                 no_graph=scenario is True)
+    exits = []
+
+    def fake_exit(code):
+        exits.append(code)
+        if threading.current_thread() is threading.main_thread():      # (the timer thread just ends)
+            raise SystemExit(code)
+    monkeypatch.setattr(bench, "hard_exit", fake_exit)
+    monkeypatch.setattr(_Graph, "replay_ms", 0.25)
+    if scenario == "replay_dies":
+        def boom():
+            raise RuntimeError("CUDA error: unspecified launch failure\nCompile with TORCH_USE_CUDA_DSA ...")
+        monkeypatch.setattr(_Graph, "on_replay", boom)
+    if scenario == "replay_hangs":
+        import time
+        monkeypatch.setattr(bench, "LATE_TIMEOUT_S", 0.3)
+        monkeypatch.setattr(_Graph, "on_replay", lambda: time.sleep(0.8) if _Graph.replays == 1 else None)
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
-        bench.run_ours(args)
-    d = json.loads([ln for ln in out.getvalue().splitlines() if ln.startswith("{")][0])
-    # a rank never replays (= executes cross-rank barriers) unless EVERY rank captured; then 2 warm replays + the steps
-    assert _Graph.replays == (0 if no_graph else 2 + 2)
-    # captured beside a live process-group watchdog thread: only this thread's calls belong to the capture
-    assert _Graph.modes == ([] if (no_graph and not failed) else ["thread_local"])
+        try:
+            bench.run_ours(args)
+        except SystemExit:
+            assert scenario == "replay_dies"
+    lines = [ln for ln in out.getvalue().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1                                   # ONE line, whatever happened to the late measurements
+    d = json.loads(lines[0])
     assert d["n_gpus"] == 2 and d["config"]["views_total"] == 4 and "copy engines" in d["config"]["parallelism"]
     assert all(t_ == sharding.BARRIER_TIMEOUT_MS for t_ in barriers) and len(barriers) > 0
-    # per step: 4 prepasses + the chunk launches of 32x32 and 16x16 (graph: 3 + 3 wave-sized chunks; eager: the two-chunk
-    # plan of round 1) + 1 + 1 in-kernel launches; the chunk launches of 1.0 "ms" each add up to one call
-    chunks = 2 if no_graph else 3
-    assert d["config"]["exchange_issue"] == ("eager" if no_graph else "one CUDA graph per step")
-    assert d["gpu_launches"] == 2 * (4 + 2 * chunks + 1 + 1), d["gpu_launches"]
-    assert d["roofline"]["ms_per_launch"] == float(chunks)
+    # captured beside a live process-group watchdog thread: only this thread's calls belong to the capture
+    assert _Graph.modes == ([] if scenario is True else ["thread_local"])
+    # Phase A always times the eagerly issued step (the two-chunk plan of round 1): per step 4 prepasses + 2 + 2 chunk
+    # launches of 32x32 / 16x16 + 1 + 1 in-kernel launches; the chunk launches of 1.0 "ms" each add up to one call.
+    eager = {"launches": 2 * (4 + 2 * 2 + 1 + 1), "ms_per_launch": 2.0, "ms_per_step": 0.5}
+    if scenario is False:
+        # phase B: the replay (3 + 3 wave-sized chunks) gave the eager step's bits and was faster -> it is the line's value
+        assert _Graph.replays == 2 + 2
+        assert d["config"]["exchange_issue"] == "one CUDA graph per step"
+        assert d["config"]["exchange_ms_per_step"] == {"eager": 0.5, "graph": 0.125, "graph_equals_eager_bitwise": True}
+        assert d["gpu_launches"] == 2 * (4 + 2 * 3 + 1 + 1) and d["ms_per_step"] == 0.125
+        assert d["roofline"]["ms_per_launch"] == 3 * 0.25
+    else:
+        assert d["config"]["exchange_issue"] == "eager"
+        assert d["gpu_launches"] == eager["launches"] and d["ms_per_step"] == eager["ms_per_step"]
+        assert d["roofline"]["ms_per_launch"] == eager["ms_per_launch"]
+        # a rank never replays (= executes cross-rank barriers) unless EVERY rank captured
+        assert _Graph.replays == {True: 0, "capture_fails": 0, "peer_capture_fails": 0, "replay_dies": 1, "replay_hangs": 4}[scenario]
+        if scenario == "capture_fails":
+            assert "capture failed on rank 0" in d["config"]["graph"]
+        if scenario == "peer_capture_fails":
+            assert d["config"]["graph"] == "capture failed on another rank"
+        if scenario == "replay_dies":                        # the held line goes out, then the process leaves
+            assert exits == [0] and "CUDA error: unspecified launch failure" in d["config"]["late_measurements"]
+        if scenario == "replay_hangs":                       # the timer printed the held line
+            assert exits == [0] and "still running after" in d["config"]["late_measurements"]
     assert "roofline_by_shape" not in d and "reference_gpu" not in d      # N = 1 extras only
 
 
@@ -252,11 +303,13 @@ def test_denoise_bench_control_flow(monkeypatch, world):
             def identity_index(self, n, device):
                 return torch.arange(n, device=device, dtype=torch.int32)
         peer = AliasPeer()
-    ms, views, ms_eager, by_views = bench.denoise_bench(torch.device("cpu"), world, 0, shard, peer, 2)
+    ms, views, ms_eager, by_views, config4 = bench.denoise_bench(torch.device("cpu"), world, 0, shard, peer, 2)
     assert ms == 0.5 and views == 2 * world            # fake events: 1.0 "ms" over 2 steps
     if world == 1:
-        assert ms_eager == 0.5 and set(by_views) == {"2", "4", "6"} and by_views["6"]["rows"] == 192
+        assert ms_eager == 0.5 and set(by_views) == {"2", "4", "6"} and by_views["6"]["rows"] == 192 and config4 is None
     else:
+        assert by_views is None
+        by_views = config4()          # run last by the caller (bench.run_ours, phase B)
         assert "error" not in by_views["config4"], by_views["config4"]
         assert by_views["config4"]["units_per_gpu"] == 12 and by_views["config4"]["views"] == 6 and by_views["config4"]["finite"]
 
