@@ -72,5 +72,7 @@ def assert_close(actual, ref, rel=2e-2, max_abs=None, what=""):
     rms = float(ref.double().pow(2).mean().sqrt())
     worst = float((actual - ref).abs().max())
     bound = (max_abs if max_abs is not None else 8 * rel) * max(rms, 1e-6)
+    if os.environ.get("CVD_TEST_VERBOSE"):      # margins for the record (pytest -s)
+        print(f"[assert_close] {what}: rel_l2={r:.3e} / {rel:.1e}, max_abs={worst:.3e} / {bound:.3e}")
     assert r <= rel and worst <= bound, f"{what}: rel_l2={r:.3e} (tol {rel:.1e}), max_abs={worst:.3e} (tol {bound:.3e}), rms={rms:.3e}"
     return r, worst

@@ -25,6 +25,12 @@ def dev():
     return test_device()
 
 
+@pytest.fixture(autouse=True)
+def fp32_convolutions(monkeypatch):
+    """The "SD blocks fp32" comparisons mean fp32: cuDNN's default TF32 convolutions are switched off for this file."""
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+
+
 @pytest.mark.parametrize("R,feat,d,n_src,kp", [(32, 32, 40, 1, 1), (32, 32, 40, 2, 1), (32, 16, 80, 2, 1), (32, 16, 40, 4, 2),
                                                (16, 64, 40, 1, 1), (32, 8, 160, 2, 1), (32, 4, 160, 2, 1)])
 def test_multi_source_and_cluster_multicast_kernels_equal_default(golden, dev, R, feat, d, n_src, kp, monkeypatch):
