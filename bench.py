@@ -582,6 +582,8 @@ def run_ours(args):
     # CVD_BENCH_DRYRUN_DEVICE exists for tests/test_bench_dryrun.py only: the CPU build box runs this function's control flow
     # with the kernels and the CUDA runtime replaced by test doubles.  The real ops refuse anything but CUDA tensors.
     dev = torch.device(os.environ.get("CVD_BENCH_DRYRUN_DEVICE", "cuda"), local)
+    # one process per GPU: keep this rank's pinned staging buffers and host threads on the GPU's own NUMA node
+    prev_affinity = sharding.bind_host_thread_near_gpu(local)
     shard = peer = None
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: if the caller asks for NCCL logging (NCCL_DEBUG=INFO, e.g. to count
@@ -883,6 +885,7 @@ def run_ours(args):
     achieved = big_flops / (big_ms * 1e-3) / 1e12
 
     line = None
+    sharding.restore_host_affinity(prev_affinity)      # the CPU baseline gets every core the box has
     if rank == 0:
         cb_times, cb_flops, cores = cpu_reference_step(R, reps=2, warm=1)
         cb_val = cb_flops / min(cb_times) / 1e12

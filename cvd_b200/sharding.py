@@ -151,3 +151,64 @@ class PeerExchange:
         if key not in self._arange:
             self._arange[key] = torch.arange(n, device=device, dtype=torch.int32)
         return self._arange[key]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Host side of the per-GPU process: staging buffers next to the GPU
+# ------------------------------------------------------------------------------------------------------------------
+def parse_cpulist(text):
+    """'0-3,8,10-11' (sysfs cpulist syntax) -> sorted list of CPU numbers."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return sorted(cpus)
+
+
+def gpu_local_cpus(device_index, sysfs="/sys"):
+    """CPUs of the NUMA node the GPU hangs off (``/sys/bus/pci/devices/<bdf>/local_cpulist``), or None when unknown."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"{sysfs}/bus/pci/devices/{bdf}/local_cpulist") as f:
+            return parse_cpulist(f.read()) or None
+    except (OSError, ValueError, AttributeError, RuntimeError, AssertionError):
+        return None
+
+
+def bind_host_thread_near_gpu(device_index, sysfs="/sys"):
+    """Restrict the calling process to the CPUs of the GPU's NUMA node, so that the pinned staging buffers it allocates
+    afterwards (first touch) and the threads that fill them sit on the socket whose PCIe root the GPU is attached to.
+    With one process per GPU on a two-socket box this keeps every rank's host<->device traffic off the inter-socket link
+    (round 1: eight ranks, 3 GB per step each, 5.4x slower per rank than one rank alone).  Returns the previous affinity
+    (hand it to ``os.sched_setaffinity(0, prev)`` to undo) or None when nothing was changed -- never an error."""
+    import os
+    try:
+        prev = os.sched_getaffinity(0)
+        local = gpu_local_cpus(device_index, sysfs)
+        want = prev & set(local or ())
+        if not want or want == prev:
+            return None
+        os.sched_setaffinity(0, want)
+        return prev
+    except (OSError, AttributeError):
+        return None
+
+
+def restore_host_affinity(prev):
+    """Undo ``bind_host_thread_near_gpu`` for EVERY thread of the process (threads created meanwhile inherited the
+    restricted set; ``sched_setaffinity`` acts per thread)."""
+    import os
+    if prev is None:
+        return
+    try:
+        tids = [int(t) for t in os.listdir("/proc/self/task")]
+    except OSError:
+        tids = [0]
+    for tid in tids:
+        try:
+            os.sched_setaffinity(tid, prev)
+        except OSError:
+            pass

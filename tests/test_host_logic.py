@@ -206,3 +206,34 @@ def test_folded_pose_conditioning_matches_reference_dataset(golden, monkeypatch)
     pl = ops.plucker_embedding(cond["intrinsics"], cond["c2w"], 256, 256).double()          # [32, 6, 256, 256], folded
     assert abs(float(pl.sum()) / float(golden["geometry"]["plucker_sum"]) - 1) < 1e-5
     assert abs(float(pl.abs().sum()) / float(golden["geometry"]["plucker_abs_sum"]) - 1) < 1e-6
+
+
+def test_gpu_local_cpu_binding_helpers(tmp_path, monkeypatch):
+    """sharding.bind_host_thread_near_gpu: sysfs cpulist parsing, intersection with the allowed set, no-ops (unknown GPU,
+    empty intersection, already inside) and the per-thread restore."""
+    import os
+    import types
+    from cvd_b200 import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and sharding.parse_cpulist("") == []
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    d = tmp_path / "bus" / "pci" / "devices" / "0000:1b:00.0"
+    d.mkdir(parents=True)
+    allowed = sorted(os.sched_getaffinity(0))
+    (d / "local_cpulist").write_text(f"{allowed[0]}\n")
+    assert sharding.gpu_local_cpus(0, str(tmp_path)) == [allowed[0]]
+    prev = sharding.bind_host_thread_near_gpu(0, str(tmp_path))
+    try:
+        if len(allowed) > 1:
+            assert prev == set(allowed) and os.sched_getaffinity(0) == {allowed[0]}
+            assert sharding.bind_host_thread_near_gpu(0, str(tmp_path)) is None          # already inside: nothing to do
+        else:
+            assert prev is None
+    finally:
+        sharding.restore_host_affinity(prev)
+    assert os.sched_getaffinity(0) == set(allowed)
+    (d / "local_cpulist").write_text("100000-100001\n")                                  # no allowed CPU on that node
+    assert sharding.bind_host_thread_near_gpu(0, str(tmp_path)) is None and os.sched_getaffinity(0) == set(allowed)
+    props.pci_bus_id = 0x2c                                                              # unknown device: no sysfs entry
+    assert sharding.gpu_local_cpus(0, str(tmp_path)) is None and sharding.bind_host_thread_near_gpu(0, str(tmp_path)) is None
+    sharding.restore_host_affinity(None)
