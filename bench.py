@@ -696,12 +696,39 @@ def run_ours(args):
         if keep["outs"] is not None:
             keep["outs"].append(o)
 
+    def slice_plan(chunks_of, runs_for):
+        """Every view the copy-engine exchange needs, cut ONCE: per shape, per call, per row chunk the (landing, peer
+        source) pairs of K and V^T and the chunk's q / landing / identity-partner views.  Issued eagerly the step is
+        host-bound (round 1), and a tensor slice costs about as much host time as a launch."""
+        plan = []
+        for (feat, _C), per_call, ld in zip(SHAPES, bufs, land):
+            calls = []
+            for q, _k, _vt, xk, xv in per_call:
+                if feat not in chunks_of:
+                    calls.append(None)
+                    continue
+                chunks = []
+                for (lo, hi), runs_c in zip(chunks_of[feat], runs_for[feat]):
+                    ck = [(ld[0][dlo:dhi], xk[2][src][slo:slo + (dhi - dlo)]) for (dlo, dhi, src, slo) in runs_c]
+                    cv = [(ld[1][dlo:dhi], xv[2][src][slo:slo + (dhi - dlo)]) for (dlo, dhi, src, slo) in runs_c]
+                    chunks.append((ck, cv, q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], ident[:hi - lo], lo, hi))
+                calls.append(chunks)
+            plan.append(calls)
+        return plan
+
+    dma = shard is not None and peer is not None and args.exchange == "dma"
+    plan_graph = slice_plan(chunk_plan, run_plan) if dma else None
+    plan_eager = slice_plan(chunk_plan_eager, run_plan_eager) if dma else None
+    in_kernel_src = None        # latents <= 8x8 read the partner's K / V^T in-kernel when it all lives on ONE peer
+    if dma and len({rk for (_, _, rk, _) in runs_whole}) == 1:
+        in_kernel_src = runs_whole[0][2]
+
     def value_step(record, eager_plan=False):
-        chunks_of, runs_for = (chunk_plan_eager, run_plan_eager) if eager_plan else (chunk_plan, run_plan)
+        plan = plan_eager if eager_plan else plan_graph
         main_stream = torch.cuda.current_stream()
-        for (feat, C), per_call, ld in zip(SHAPES, bufs, land):
+        for si, ((feat, C), per_call, ld) in enumerate(zip(SHAPES, bufs, land)):
             rec = record and feat == SHAPES[0][0]
-            for q, k, vt, xk, xv in per_call:
+            for ci, (q, k, vt, xk, xv) in enumerate(per_call):
                 if rec:
                     big_events.append([])
                 rowp = ops.epi_row_params(F_rows, feat, F_MAT_SIZE, theta, _lib.FF_RANDOM_SLOPE)
@@ -712,31 +739,32 @@ def run_ours(args):
                 elif args.exchange == "dma":
                     # one cross-rank barrier (the partner's K / V^T of this call are complete) ...
                     sharding.barrier(xk[1])
-                    if feat * feat <= 64 and len({rk for (_, _, rk, _) in runs_whole}) == 1:
+                    if feat * feat <= 64 and in_kernel_src is not None:
                         # ... then, one query tile per (row, head): the kernel reads the partner's K / V^T tiles straight
                         # out of the peer's HBM (unicast TMA over NVLink, plain loads at 4x4) -- every byte crosses once,
                         # no landing buffer, no copy launch
-                        src = runs_whole[0][2]
-                        timed_attn(False, q, xk[2][src], xv[2][src], rowp, partner_local, HEADS, F_MAT_SIZE)
+                        timed_attn(False, q, xk[2][in_kernel_src], xv[2][in_kernel_src], rowp, partner_local, HEADS, F_MAT_SIZE)
                         continue
                     # ... then the partner rows cross NVLink on the COPY ENGINES in row chunks (K and V^T on two side
                     # streams), each chunk's attention running under the transfer of the next (no SMs spent on the pull)
+                    chunks = plan[si][ci]
                     ev_b.record(main_stream)
                     side_k.wait_event(ev_b)
                     side_v.wait_event(ev_b)
-                    for c, runs_c in enumerate(runs_for[feat]):
-                        with torch.cuda.stream(side_k):
-                            for (dlo, dhi, src_rank, slo) in runs_c:
-                                ld[0][dlo:dhi].copy_(xk[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
+                    with torch.cuda.stream(side_k):
+                        for c, ch in enumerate(chunks):
+                            for dst, src_ in ch[0]:
+                                dst.copy_(src_, non_blocking=True)
                             ev_k[c].record(side_k)
-                        with torch.cuda.stream(side_v):
-                            for (dlo, dhi, src_rank, slo) in runs_c:
-                                ld[1][dlo:dhi].copy_(xv[2][src_rank][slo:slo + (dhi - dlo)], non_blocking=True)
+                    with torch.cuda.stream(side_v):
+                        for c, ch in enumerate(chunks):
+                            for dst, src_ in ch[1]:
+                                dst.copy_(src_, non_blocking=True)
                             ev_v[c].record(side_v)
-                    for c, (lo, hi) in enumerate(chunks_of[feat]):
+                    for c, (_ck, _cv, q_c, lk_c, lv_c, id_c, lo, hi) in enumerate(chunks):
                         main_stream.wait_event(ev_k[c])
                         main_stream.wait_event(ev_v[c])
-                        timed_attn(rec, q[lo:hi], ld[0][lo:hi], ld[1][lo:hi], rowp[lo:hi], ident[:hi - lo], HEADS, F_MAT_SIZE)
+                        timed_attn(rec, q_c, lk_c, lv_c, rowp[lo:hi], id_c, HEADS, F_MAT_SIZE)
                 else:                         # one cross-rank barrier, then pull only the partner rows over NVLink (SM kernel)
                     ks = peer.pull(xk[0], xk[1], partner, ld[0], rows_per_src=R)
                     vs = ops.peer_gather_rows(xv[0], partner, ld[1], rows_per_src=R)
