@@ -63,6 +63,14 @@ class DDIMSchedule:
         pred_x0 = (sample - (1.0 - a_t) ** 0.5 * model_output) / a_t ** 0.5
         return a_prev ** 0.5 * pred_x0 + (1.0 - a_prev) ** 0.5 * model_output
 
+    def add_noise(self, original_samples, noise, timesteps):
+        """The forward diffusion the training step applies (``train_epi_control.py:555`` -> diffusers ``add_noise``):
+        ``sqrt(a_t) x + sqrt(1 - a_t) noise`` with one timestep per sample (``timesteps`` int [B], broadcast over the
+        remaining dimensions)."""
+        a = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)[timesteps.to(original_samples.device)]
+        a = a.reshape(-1, *([1] * (original_samples.ndim - 1)))
+        return a ** 0.5 * original_samples + (1.0 - a) ** 0.5 * noise
+
     def renoise(self, latents, t, noise):
         """pipeline_animation_epi_advanced.py:700-705: back from t_prev to t between multistep repeats.
         (``alphas_cumprod[prev_t]`` with Python indexing, negative ``prev_t`` included, like the reference.)"""

@@ -11,11 +11,17 @@ reverse parameter order (the order autograd finishes them in), and unpacked aver
     opt.zero_grad(set_to_none=True); loss.backward()
     cvd_b200.training.allreduce_gradients(trainable)            # NCCL over NVLink; gloo in the CPU tests
     torch.nn.utils.clip_grad_norm_(trainable, max_grad_norm); opt.step()
+
+The step itself (``train_epi_control.py:245-259`` freeze, ``:548-630`` step, from the latents on -- VAE and text encoder
+are out of scope) is ``freeze_for_sync_training`` + ``PoseAdaptor`` + ``training_step``; pinned on the CPU against the
+reference's own UNet / PoseAdaptor executed verbatim (tests/golden/train_step.npz).
 """
 from typing import Iterable, List
 
 import torch
 import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
 
 
 def trainable_epi_parameters(module) -> List[torch.nn.Parameter]:
@@ -62,3 +68,66 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, comm_d
             p.grad.copy_((flat[off:off + n].to(torch.float32) / world).view_as(p.grad))
             off += n
     return len(buckets)
+
+
+def freeze_for_sync_training(unet, pose_encoder=None) -> List[str]:
+    """``train_epi_control.py:245-259``: everything frozen except the parameters whose name contains ``epi_modules``,
+    ``sync`` or ``auxiliary``.  Returns the trainable names in ``named_parameters`` order (the checkpoint's
+    ``unet_trainable_dict`` keys, ``:647-653``)."""
+    unet.requires_grad_(False)
+    if pose_encoder is not None:
+        pose_encoder.requires_grad_(False)
+    names = []
+    for name, param in unet.named_parameters():
+        if "epi_modules" in name or "sync" in name or "auxiliary" in name:
+            param.requires_grad = True
+            names.append(name)
+    return names
+
+
+class PoseAdaptor(nn.Module):
+    """``animatediff/models/pose_adaptor.py:81-104``: pose encoder in front of the UNet; returns ``(noise_pred, auxiliary)``."""
+
+    def __init__(self, unet, pose_encoder):
+        super().__init__()
+        self.unet = unet
+        self.pose_encoder = pose_encoder
+
+    def forward(self, noisy_latents, timesteps, encoder_hidden_states, pose_embedding, F_mats=None, H_mats=None):
+        feats = None
+        if pose_embedding is not None:
+            assert pose_embedding.ndim == 5
+            bs = pose_embedding.shape[0]                                     # b c f h w
+            feats = [x.reshape(bs, x.shape[0] // bs, *x.shape[1:]).permute(0, 2, 1, 3, 4)      # (b f) c h w -> b c f h w
+                     for x in self.pose_encoder(pose_embedding)]
+        out = self.unet(noisy_latents, timesteps, encoder_hidden_states, F_mats=F_mats, H_mats=H_mats,
+                        pose_embedding_features=feats)
+        return out.sample, out.auxiliary
+
+
+def training_step(pose_adaptor, optimizer, schedule, latents, noise, timesteps, encoder_hidden_states,
+                  plucker_embedding=None, F_mats=None, H_mats=None, warped_masks=None, max_grad_norm=1.0, group=None,
+                  comm_dtype=torch.bfloat16):
+    """One optimisation step of the sync modules, from the latents on (``train_epi_control.py:548-630``, the
+    ``mixed_precision_training=False`` branch; this package's UNet applies bf16 autocast to its SD blocks itself):
+
+    forward diffusion of ``latents`` [b, c, f, h, w] at ``timesteps`` [b] -> epsilon prediction -> MSE against ``noise``
+    (both sides multiplied by ``warped_masks`` when the batch carries homographies, ``:536-545``) -> backward -> gradient
+    average over ``group`` (what DistributedDataParallel does for the reference, ``:349``; skipped in a single process)
+    -> clip to ``max_grad_norm`` -> ``optimizer.step()`` -> ``zero_grad(set_to_none=True)``.
+    Returns ``(loss, total_grad_norm)`` as detached tensors."""
+    trainable = trainable_epi_parameters(pose_adaptor)
+    noisy = schedule.add_noise(latents, noise, timesteps)
+    pred, auxiliary = pose_adaptor(noisy, timesteps, encoder_hidden_states, plucker_embedding, F_mats=F_mats, H_mats=H_mats)
+    if auxiliary is not None:
+        raise NotImplementedError("the auxiliary head (additional_channel > 0) is not built: the reference's loss for it "
+                                  "(tools/consistency_losses.py, train_epi_control.py:38) is not part of the reference tree")
+    mask = torch.ones_like(latents) if warped_masks is None else warped_masks
+    loss = F.mse_loss(pred.float() * mask, noise.float() * mask, reduction="mean")
+    loss.backward()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        allreduce_gradients(trainable, group=group, comm_dtype=comm_dtype)
+    total_norm = torch.nn.utils.clip_grad_norm_(trainable, max_grad_norm)
+    optimizer.step()
+    optimizer.zero_grad(set_to_none=True)
+    return loss.detach(), total_norm.detach()

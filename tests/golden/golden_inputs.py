@@ -232,3 +232,22 @@ def unet_multiview_inputs(V=4, seed=UNET_SEED + 50, feat=8, channels=(32, 64), t
              for i, c in enumerate(channels)]
     noises = [torch.from_numpy(rs.standard_normal((V, 4, 16, feat, feat)).astype(np.float32)) for _ in range(8)]
     return lat, text, poses, noises
+
+
+# ---- one optimisation step of the sync modules (train_epi_control.py:245-259, :548-630) at the reduced UNet width -----------
+TRAIN_POSE_ENCODER_KWARGS = dict(downscale_factor=2, channels=[32, 64], nums_rb=2, cin=24, ksize=1, sk=True, use_conv=False,
+                                 compression_factor=1, temporal_attention_nhead=4, attention_block_types=["Temporal_Self"],
+                                 temporal_position_encoding=True, temporal_position_encoding_max_len=16)
+TRAIN_GPU_POSE_ENCODER_KWARGS = dict(TRAIN_POSE_ENCODER_KWARGS, channels=[320, 640], temporal_attention_nhead=8)      # device widths
+TRAIN_SEED = 8900
+TRAIN_OPT = dict(lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)      # the script's AdamW (:275-281), larger lr
+TRAIN_MAX_GRAD_NORM = 0.1
+TRAIN_TIMESTEPS = (481, 37)
+
+
+def train_inputs(seed=TRAIN_SEED, feat=8):
+    """noise [2,4,16,f,f], one timestep per video, Pluecker-like embedding [2,6,16,2f,2f] (pose encoder downscale 2)."""
+    rs = np.random.RandomState(seed)
+    noise = torch.from_numpy(rs.standard_normal((2, 4, 16, feat, feat)).astype(np.float32))
+    plucker = torch.from_numpy(rs.standard_normal((2, 6, 16, 2 * feat, 2 * feat)).astype(np.float32))
+    return noise, torch.tensor(TRAIN_TIMESTEPS, dtype=torch.long), plucker

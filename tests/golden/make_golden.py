@@ -362,6 +362,68 @@ def unet_gpu(Fm):
     save("unet_gpu", **out)
 
 
+def train_step(Fm, gpu=False):
+    """(``gpu``: the same at widths 320 / 640, the shapes the device kernels are instantiated for -> train_step_gpu.npz.)
+    One optimisation step of the reference's training loop on the reference's own modules: the freeze of
+    train_epi_control.py:245-259, PoseAdaptor(unet, pose_encoder) (pose_adaptor.py:81-104), and the statements of
+    :548-630 from the latents on (mixed_precision_training=False branch; forward diffusion by the published add_noise
+    formula -- diffusers' scheduler is not installable here).  The fixture holds the loss, the total gradient norm,
+    per-parameter gradient norms and update norms, and three updated parameters."""
+    import torch.nn.functional as F
+    from animatediff.models.pose_adaptor import CameraPoseEncoder, PoseAdaptor
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    ukw, pkw, useed = (gi.UNET_GPU_KWARGS, gi.UNET_GPU_PROCESSOR_KWARGS, gi.UNET_GPU_SEED) if gpu else \
+        (gi.UNET_KWARGS, gi.UNET_PROCESSOR_KWARGS, gi.UNET_SEED)
+    unet_ = UNet3DConditionModelPoseCond(**ukw)
+    unet_.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                                 motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                                 sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                                 **pkw)
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    shapes = {k: tuple(v.shape) for k, v in unet_.state_dict().items() if not k.endswith(skip)}
+    unet_.load_state_dict(gi.fill_state_dict(shapes, useed), strict=False)
+    enc = CameraPoseEncoder(**(gi.TRAIN_GPU_POSE_ENCODER_KWARGS if gpu else gi.TRAIN_POSE_ENCODER_KWARGS))
+    eshapes = {k: tuple(v.shape) for k, v in enc.state_dict().items() if not k.endswith("pos_encoder.pe")}
+    enc.load_state_dict(gi.fill_state_dict(eshapes, gi.TRAIN_SEED + 1), strict=False)
+    # train_epi_control.py:245-259
+    unet_.requires_grad_(False)
+    enc.requires_grad_(False)
+    for name, param in unet_.named_parameters():
+        if "epi_modules" in name or "sync" in name or "auxiliary" in name:
+            param.requires_grad = True
+    pose_adaptor = PoseAdaptor(unet_, enc)
+    names = [k for k, v in unet_.named_parameters() if v.requires_grad]
+    params = [v for k, v in unet_.named_parameters() if v.requires_grad]
+    optimizer = torch.optim.AdamW(params, **gi.TRAIN_OPT)
+    pose_adaptor.train()
+    lat, text, _poses = gi.unet_inputs(gi.UNET_GPU_SEED, channels=(320, 640), text_dim=64) if gpu else gi.unet_inputs()
+    noise, timesteps, plucker = gi.train_inputs()
+    F2 = Fm.reshape(2, 16, 3, 3)
+    betas = torch.linspace(0.00085, 0.012, 1000, dtype=torch.float32)
+    ac = torch.cumprod(1.0 - betas, dim=0)[timesteps].reshape(-1, 1, 1, 1, 1)
+    noisy = ac ** 0.5 * lat + (1.0 - ac) ** 0.5 * noise
+    before = [p.detach().clone() for p in params]
+    with torch.enable_grad():
+        model_pred, auxiliary = pose_adaptor(noisy, timesteps, encoder_hidden_states=text, pose_embedding=plucker,
+                                             F_mats=F2, H_mats=None)
+        assert auxiliary is None
+        warped_masks = torch.ones_like(lat)
+        loss = F.mse_loss(model_pred.float() * warped_masks, noise.float() * warped_masks, reduction="mean")
+        loss.backward()
+    grad_norms = torch.stack([p.grad.norm() for p in params])
+    total = torch.nn.utils.clip_grad_norm_(filter(lambda p: p.requires_grad, pose_adaptor.parameters()), gi.TRAIN_MAX_GRAD_NORM)
+    optimizer.step()
+    deltas = torch.stack([(p.detach() - b).norm() for p, b in zip(params, before)])
+    small = [i for i, p in enumerate(params) if p.numel() <= 4096]
+    picks = [small[0], small[len(small) // 2], small[-1]]
+    out = {"names": np.array(names), "loss": loss.detach(), "total_norm": total, "grad_norms": grad_norms, "delta_norms": deltas,
+           "model_pred": model_pred.detach(), "picks": np.array(picks)}
+    for j, i in enumerate(picks):
+        out[f"after{j}"] = params[i].detach()
+    print(f"train_step: {len(names)} trainable tensors, loss {float(loss):.5f}, grad norm {float(total):.4f}")
+    save("train_step_gpu" if gpu else "train_step", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -383,7 +445,11 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step"):
+        if sys.argv[1] == "train_step":
+            train_step(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
+            train_step(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]), gpu=True)
+            sys.exit(0)
         if sys.argv[1] == "unet":
             unet(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
             unet_gpu(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
@@ -401,3 +467,5 @@ if __name__ == "__main__":
     pose_encoder()
     unet(Fm)
     unet_gpu(Fm)
+    train_step(Fm)
+    train_step(Fm, gpu=True)

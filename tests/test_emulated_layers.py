@@ -512,3 +512,18 @@ def test_pair_pipeline_from_pose_files_to_latents(monkeypatch):
                                       pose_embedding_features=feats)
     assert [tuple(f.shape) for f in feats] == [(2, 32, 16, 8, 8), (2, 64, 16, 4, 4)]
     assert torch.equal(out, ref_out)
+
+
+@pytest.mark.parametrize("device_widths", [False, True])
+def test_unet_training_step_vs_reference_training_step(golden, monkeypatch, device_widths):
+    """BASELINE config 5 at the UNet level: cvd_b200.training (freeze_for_sync_training + PoseAdaptor + training_step) on the
+    product UNet and pose encoder against ONE optimisation step of the reference's loop on the reference's own modules
+    (train_epi_control.py:245-259, :548-630 and pose_adaptor.py:81-104 executed on models/unet.py verbatim,
+    tests/golden/train_step*.npz): same trainable set, loss, epsilon prediction, total and per-parameter gradient norms
+    (clipping active: max_grad_norm 0.1 < norm), AdamW update norms and three updated tensors.  Kernels emulated (bf16
+    roundings of the device path), SD blocks fp32.  ``device_widths``: the fixture the B200 test uses (widths 320 / 640),
+    under the strict device-shape rules -- a failure there on hardware then points at the kernels."""
+    from train_case import run_training_step_case
+    emulated_ops.install(monkeypatch, strict_shapes=device_widths)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))     # the train twins refuse CPU tensors
+    run_training_step_case(torch.device("cpu"), t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3), device_widths, REL)

@@ -205,3 +205,13 @@ def test_multiview_ddim_final_latents_vs_reference_unet_on_device(dev):
                                          aux_K_mats=K, pose_embedding_features=[p.to(dev) for p in poses4], multistep=2,
                                          noise_fn=lambda shape: next(it).to(dev))
     assert_close(final, torch.from_numpy(g["mv_final"]), rel=5e-2, what="multiview ddim final latents")
+
+
+def test_unet_training_step_vs_reference_training_step_on_device(golden, dev):
+    """BASELINE config 5 at the UNet level on the B200: one optimisation step of cvd_b200.training (product UNet at widths
+    320 / 640 + pose encoder; tcgen05 forward with lse, mma.sync backward, glue through torch autograd twins, AdamW) against
+    the reference's own loop on the reference's modules (tests/golden/train_step_gpu.npz) -- loss, epsilon prediction,
+    gradient norms per parameter, clipping, update.  The same case runs with emulated kernels on the CPU
+    (tests/test_emulated_layers.py)."""
+    from train_case import run_training_step_case
+    run_training_step_case(dev, torch.from_numpy(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3), True, REL)

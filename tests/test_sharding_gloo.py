@@ -105,3 +105,63 @@ def test_gradient_allreduce_world2_equals_mean_of_rank_gradients():
         p.grad = torch.zeros_like(p)
     sizes = [[p.numel() for p in b] for b in training.gradient_buckets(ps, 1200, 2)]
     assert sizes == [[500, 20], [300, 10]]                       # reverse parameter order, greedy 600-element buckets
+
+
+class _ToyAdaptor(torch.nn.Module):
+    """Stand-in with PoseAdaptor's call signature: a per-pixel linear epsilon predictor (returns (pred, auxiliary=None))."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.mix = torch.nn.Conv3d(4, 4, 1)
+        self.frozen = torch.nn.Conv3d(4, 4, 1).requires_grad_(False)
+
+    def forward(self, noisy_latents, timesteps, encoder_hidden_states, pose_embedding, F_mats=None, H_mats=None):
+        return self.mix(self.frozen(noisy_latents)) + encoder_hidden_states.mean(), None
+
+
+def _step_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cvd_b200 import sampler, training
+        net = _ToyAdaptor()
+        opt = torch.optim.SGD(training.trainable_epi_parameters(net), lr=0.5)
+        g = torch.Generator().manual_seed(200 + rank)            # every rank its own batch
+        lat, noise = torch.randn(2, 4, 3, 4, 4, generator=g), torch.randn(2, 4, 3, 4, 4, generator=g)
+        ts = torch.tensor([900 - 100 * rank, 17 + rank])
+        loss, total = training.training_step(net, opt, sampler.DDIMSchedule(), lat, noise, ts, torch.ones(2, 3, 5),
+                                             max_grad_norm=0.05, comm_dtype=torch.float32)
+        ret[rank] = (float(loss), float(total), [p.detach().numpy().copy() for p in net.parameters()])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_step_world2_equals_one_process_on_the_joint_batch():
+    """cvd_b200.training.training_step under gloo, world 2: gradients are averaged across the ranks BEFORE clipping and the
+    optimizer step (what DistributedDataParallel does for train_epi_control.py:349,612-630), so both ranks end with the
+    same parameters -- those one process reaches with the mean of the two ranks' losses."""
+    from cvd_b200 import sampler, training
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_step_worker, args=(2, port, ret), nprocs=2, join=True)
+    (loss0, tot0, p0), (loss1, tot1, p1) = ret[0], ret[1]
+    assert abs(tot0 - tot1) < 1e-6 and all(np.array_equal(a, b) for a, b in zip(p0, p1)) and loss0 != loss1
+    net = _ToyAdaptor()
+    params = training.trainable_epi_parameters(net)
+    sch = sampler.DDIMSchedule()
+    total_loss = 0.0
+    for rank in range(2):
+        g = torch.Generator().manual_seed(200 + rank)
+        lat, noise = torch.randn(2, 4, 3, 4, 4, generator=g), torch.randn(2, 4, 3, 4, 4, generator=g)
+        ts = torch.tensor([900 - 100 * rank, 17 + rank])
+        pred, _ = net(sch.add_noise(lat, noise, ts), ts, torch.ones(2, 3, 5), None)
+        total_loss = total_loss + torch.nn.functional.mse_loss(pred, noise) / 2
+    total_loss.backward()
+    tot = torch.nn.utils.clip_grad_norm_(params, 0.05)
+    torch.optim.SGD(params, lr=0.5).step()
+    assert abs(float(tot) - tot0) < 1e-5 and float(tot) > 0.05          # clipping active
+    for a, b in zip(p0, net.parameters()):
+        assert np.allclose(a, b.detach().numpy(), atol=1e-6)
