@@ -21,6 +21,6 @@ from .motion_module import (AttnProcessor, PoseAdaptorAttnProcessor, PositionalE
 
 from .pose_encoder import CameraPoseEncoder  # noqa: F401
 from .unet import UNet3DConditionModelPoseCond  # noqa: F401
-from .pipeline import PairPipeline  # noqa: F401
+from .pipeline import MultiviewPipeline, PairPipeline  # noqa: F401
 
 __version__ = "0.2.0"

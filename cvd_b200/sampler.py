@@ -328,24 +328,30 @@ def install_sharding(module, shard, peer=None):
     return n
 
 
-def multiview_cameras(view_num, video_length=FRAMES, cam_pattern="circle", camera_dist=0.5, image_size=256):
-    """Synthetic V-view camera rigs of ``inference_epi_advanced.py:293-343`` (patterns ``circle`` and
-    ``upper_hemi``; every trajectory runs from the identity pose to the view's target pose,
-    :func:`interpolate_pose` without perturbation).  Returns (c2w [V*f,4,4] float32, K [V*f,3,3] float32)."""
+def multiview_cameras(view_num, video_length=FRAMES, cam_pattern="circle", camera_dist=0.5, image_size=256, image_height=None):
+    """Synthetic V-view camera rigs of ``inference_epi_advanced.py:293-343`` (patterns ``circle``, ``upper_hemi`` and
+    ``interpolate``; every trajectory runs from the identity pose to the view's target pose, :func:`interpolate_pose`
+    without perturbation).  ``image_size`` is the image width (and height unless ``image_height`` is given): the 256-pixel
+    intrinsics are scaled per axis (``:299-300``).  Returns (c2w [V*f,4,4] float32, K [V*f,3,3] float32)."""
     import math
     K = np.array([[223.578, 0, 128], [0, 223.578, 128], [0, 0, 1]], dtype=np.float64)
     K = np.repeat(K[None], view_num * video_length, axis=0)
     K[:, 0] *= image_size / 256
-    K[:, 1] *= image_size / 256
+    K[:, 1] *= (image_size if image_height is None else image_height) / 256
     out = []
     for i in range(view_num):
         if cam_pattern == "upper_hemi":
             angle = math.pi / (view_num - 1) * i + math.pi
         elif cam_pattern == "circle":
             angle = 2 * math.pi / view_num * i
+        elif cam_pattern == "interpolate":
+            angle = math.pi / (view_num - 1) * i
         else:
             raise ValueError(cam_pattern)
-        cam_at = np.array([math.cos(angle), math.sin(angle), 0]) * camera_dist
+        if cam_pattern == "interpolate":                  # :302-309: a shallow arc in front of the scene
+            cam_at = np.array([math.cos(angle), math.cos(angle + 0.5) * 0.3, -math.sin(angle) * 0.2]) * camera_dist
+        else:
+            cam_at = np.array([math.cos(angle), math.sin(angle), 0]) * camera_dist
         cam_z = np.array([0, 0, 1]) - cam_at
         cam_x = np.array([1, 0, 0])
         cam_y = np.cross(cam_z, cam_x)

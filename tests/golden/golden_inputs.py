@@ -251,3 +251,12 @@ def train_inputs(seed=TRAIN_SEED, feat=8):
     noise = torch.from_numpy(rs.standard_normal((2, 4, 16, feat, feat)).astype(np.float32))
     plucker = torch.from_numpy(rs.standard_normal((2, 6, 16, 2 * feat, 2 * feat)).astype(np.float32))
     return noise, torch.tensor(TRAIN_TIMESTEPS, dtype=torch.long), plucker
+
+
+# ---- the V-view generation path from the camera rig to the final latents (inference_epi_advanced.py:293-354 + pipeline) ------
+PIPE_POSE_ENCODER_KWARGS = dict(downscale_factor=8, channels=[32, 64], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False,
+                                compression_factor=1, temporal_attention_nhead=8, attention_block_types=["Temporal_Self"],
+                                temporal_position_encoding=True, temporal_position_encoding_max_len=16)
+PIPE_MV = dict(view_num=4, cam_pattern="interpolate", camera_dist=0.5, height=64, width=64, num_inference_steps=3,
+               guidance_scale=4.0, multistep=2, accumulate_step=2)
+PIPE_SEED = 9100

@@ -424,6 +424,65 @@ def train_step(Fm, gpu=False):
     save("train_step_gpu" if gpu else "train_step", **out)
 
 
+def pipeline_mv():
+    """The V-view generation path end to end on the reference's own code: camera rig, intrinsics and Pluecker rays by
+    EXECUTING inference_epi_advanced.py:110-128,294-354 (rig 'interpolate', 4 views, 64x64 images; and a non-square
+    64x32 rig for the per-axis intrinsics scaling), the reference's CameraPoseEncoder, and the oracle restatement of
+    pipeline_animation_epi_advanced.py:596-705 (multistep 2, accumulate 2, guidance 4) driving the reference's UNet."""
+    import math as _math
+    import types
+    from einops import rearrange
+    from scipy.spatial.transform import Rotation as R, Slerp
+    from animatediff.data.dataset_validation import ray_condition
+    from animatediff.models.pose_adaptor import CameraPoseEncoder
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    from oracle import sampler_oracle as SO
+    cam_fn_src = _ref_lines("inference_epi_advanced.py", 110, 128)
+    rig_src = _ref_lines("inference_epi_advanced.py", 294, 354)
+    cfg = gi.PIPE_MV
+
+    def rig(width, height):
+        ns = {"np": np, "math": _math, "R": R, "Slerp": Slerp, "torch": torch, "ray_condition": ray_condition,
+              "rearrange": rearrange, "device": "cpu",
+              "pipeline": types.SimpleNamespace(unet=types.SimpleNamespace(device="cpu"))}
+        exec(cam_fn_src, ns)
+        ns["args"] = types.SimpleNamespace(view_num=cfg["view_num"], video_length=16, image_width=width, image_height=height,
+                                           cam_pattern=cfg["cam_pattern"], camera_dist=cfg["camera_dist"], cam_perturb_traj=0.0)
+        exec(rig_src, ns)
+        return ns["c2ws"][0], ns["K_mats"][0], ns["plucker_embedding"]        # [Vf,4,4], [Vf,3,3], [V,6,f,H,W]
+    out = {}
+    c2w_ns, K_ns, pl_ns = rig(64, 32)
+    out["ns_c2w"], out["ns_K"], out["ns_plucker_sub"] = c2w_ns, K_ns, pl_ns[:, :, ::5, ::7, ::9]
+    c2w, K, pl = rig(cfg["width"], cfg["height"])
+    out["c2w"], out["K"], out["plucker_sub"] = c2w, K, pl[:, :, ::5, ::9, ::9]
+    m = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    m.eval()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_SEED), strict=False)
+    enc = CameraPoseEncoder(**gi.PIPE_POSE_ENCODER_KWARGS).eval()
+    eshapes = {k: tuple(v.shape) for k, v in enc.state_dict().items() if not k.endswith("pos_encoder.pe")}
+    enc.load_state_dict(gi.fill_state_dict(eshapes, gi.PIPE_SEED), strict=False)
+    V = cfg["view_num"]
+    feats = [rearrange(x, "(b f) c h w -> b c f h w", b=V) for x in enc(pl)]          # pipeline :583-586
+    out["feat0_sub"], out["feat1"] = feats[0][:, ::4, ::5], feats[1][:, ::8, ::5]
+    lat4, text4, _poses4, noises = gi.unet_multiview_inputs(V, seed=gi.PIPE_SEED + 1)
+    it = iter(noises)
+    np.random.seed(77)
+
+    def call(x, t, **kw):
+        return m(x, t, encoder_hidden_states=kw.get("encoder_hidden_states"), F_mats=kw.get("F_mats"),
+                 pose_embedding_features=kw.get("pose_embedding_features")).sample
+    out["final"] = SO.sample_multiview(call, lat4.clone(), text4, cfg["num_inference_steps"], cfg["guidance_scale"],
+                                       c2w.numpy(), K.numpy(), feats, multistep=cfg["multistep"], accumulate=cfg["accumulate_step"],
+                                       noise_fn=lambda shape: next(it))
+    save("pipeline_mv", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -445,7 +504,10 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv"):
+        if sys.argv[1] == "pipeline_mv":
+            pipeline_mv()
+            sys.exit(0)
         if sys.argv[1] == "train_step":
             train_step(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
             train_step(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]), gpu=True)
@@ -469,3 +531,4 @@ if __name__ == "__main__":
     unet_gpu(Fm)
     train_step(Fm)
     train_step(Fm, gpu=True)
+    pipeline_mv()

@@ -527,3 +527,48 @@ def test_unet_training_step_vs_reference_training_step(golden, monkeypatch, devi
     emulated_ops.install(monkeypatch, strict_shapes=device_widths)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))     # the train twins refuse CPU tensors
     run_training_step_case(torch.device("cpu"), t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3), device_widths, REL)
+
+
+def test_multiview_pipeline_from_camera_rig_to_latents(monkeypatch):
+    """cvd_b200.MultiviewPipeline -- camera rig ('interpolate', 4 views) -> intrinsics -> Pluecker rays -> pose encoder ->
+    V-view loop (multistep 2, accumulate 2, guidance 4) -- against the same path on the REFERENCE's own code
+    (tests/golden/pipeline_mv.npz: inference_epi_advanced.py:294-354 executed line by line, the reference's
+    CameraPoseEncoder and UNet, the oracle restatement of the loop): cameras, per-axis intrinsics scaling (64x32 rig),
+    rays, pose features and the final latents.  Kernels emulated, reduced-width UNet."""
+    import cvd_b200
+    from cvd_b200 import sampler
+    emulated_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))     # the pose encoder refuses CPU tensors
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pipeline_mv.npz"))
+    cfg = gi.PIPE_MV
+    # rigs
+    c2w, K = sampler.multiview_cameras(cfg["view_num"], 16, cfg["cam_pattern"], cfg["camera_dist"], cfg["width"], cfg["height"])
+    np.testing.assert_allclose(c2w, g["c2w"], atol=1e-6)
+    np.testing.assert_allclose(K, g["K"], atol=1e-4)
+    c2w_ns, K_ns = sampler.multiview_cameras(cfg["view_num"], 16, cfg["cam_pattern"], cfg["camera_dist"], 64, 32)
+    np.testing.assert_allclose(c2w_ns, g["ns_c2w"], atol=1e-6)
+    np.testing.assert_allclose(K_ns, g["ns_K"], atol=1e-4)
+    unet = _product_unet()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in unet.state_dict().items() if not k.endswith(skip)}
+    unet.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    enc = cvd_b200.CameraPoseEncoder(**gi.PIPE_POSE_ENCODER_KWARGS).eval()
+    eshapes = {k: tuple(v.shape) for k, v in enc.state_dict().items() if not k.endswith("pos_encoder.pe")}
+    enc.load_state_dict(gi.fill_state_dict(eshapes, gi.PIPE_SEED), strict=False)
+    pipe = cvd_b200.MultiviewPipeline(unet, enc)
+    # rays and pose features (incl. the non-square rig)
+    from cvd_b200 import ops
+    intr = torch.stack([t(K_ns)[:, 0, 0], t(K_ns)[:, 1, 1], t(K_ns)[:, 0, 2], t(K_ns)[:, 1, 2]], dim=1)
+    pl_ns = ops.plucker_embedding(intr, t(c2w_ns), 32, 64).view(4, 16, 6, 32, 64).permute(0, 2, 1, 3, 4)
+    np.testing.assert_allclose(pl_ns[:, :, ::5, ::7, ::9].numpy(), g["ns_plucker_sub"], atol=2e-5)
+    feats = pipe.pose_features(c2w, K, cfg["height"], cfg["width"], 16, torch.device("cpu"))
+    assert [tuple(f.shape) for f in feats] == [(4, 32, 16, 8, 8), (4, 64, 16, 4, 4)]
+    assert rel_l2(feats[0][:, ::4, ::5], t(g["feat0_sub"])) < REL and rel_l2(feats[1][:, ::8, ::5], t(g["feat1"])) < REL
+    # end to end
+    lat4, text4, _poses4, noises = gi.unet_multiview_inputs(cfg["view_num"], seed=gi.PIPE_SEED + 1)
+    it = iter(noises)
+    np.random.seed(77)
+    out = pipe(text4[:2], latents=lat4.clone(), noise_fn=lambda shape: next(it), **cfg)
+    err = rel_l2(out, t(g["final"]))
+    assert out.shape == lat4.shape and err < 5e-2, err
+    print(f"multiview pipeline final latents rel_l2 {err:.2e}")
