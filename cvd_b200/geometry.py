@@ -111,6 +111,52 @@ def folded_pose_conditioning(pose_file_0, pose_file_1, sample_n_frames=16, sampl
                 fold_indices=fold, c2w_all=c2w, intrinsics_all=intrinsics)
 
 
+def sample_clip_frames(total_frames, sample_n_frames=16, sample_stride=8, rng=None):
+    """The 2n-1 frame numbers the TRAINING dataset draws from a clip (dataset_train_realestate10k.py:399-406): an evenly
+    strided window at a random start (ONE ``random.randint`` from Python's global RNG, like the reference)."""
+    import random
+    rng = random if rng is None else rng
+    sample_length = sample_n_frames * 2 - 1
+    assert total_frames >= sample_length
+    stride = min(total_frames // sample_length, sample_stride)
+    clip_length = min(total_frames, (sample_length - 1) * stride + 1)
+    start = rng.randint(0, total_frames - clip_length)
+    return np.linspace(start, start + clip_length - 1, sample_length, dtype=int)
+
+
+def folded_clip_conditioning(pose_file, frame_indices, image_hw, sample_n_frames=16, sample_size=256):
+    """Everything ``RealEstate10KPoseFolded.get_batch`` of the TRAINING dataset derives from the camera file of one clip
+    (dataset_train_realestate10k.py:408-474): the 2n-1 cameras ``frame_indices`` made relative to the middle one (float32,
+    :437), pixel intrinsics of the centre-cropped ``sample_size`` image from the clip's real image size ``image_hw``
+    (:421-425), F of frame n-1-i -> frame n-1+i and its transpose for the way back (:451-462), and the FOLDED camera list
+    (video 0 runs from the middle frame backwards, video 1 forwards, :463-469) whose Pluecker rays condition the two videos.
+    Returns the same dictionary as :func:`folded_pose_conditioning` (``F_mats`` [2n,3,3], ``c2w`` [2n,4,4], ``K`` [2n,3,3],
+    ``intrinsics`` [2n,4])."""
+    cams = read_pose_file(pose_file)
+    cams = [cams[int(i)] for i in frame_indices]
+    n = sample_n_frames
+    assert len(cams) == 2 * n - 1
+    H, W = image_hw
+    crop = min(H, W)
+    rescale = sample_size / crop
+    dH, dW = (H - crop) / 2, (W - crop) / 2
+    K = np.array([[[W * rescale * c.fx, 0, (W * c.cx - dW) * rescale],
+                   [0, H * rescale * c.fy, (H * c.cy - dH) * rescale],
+                   [0, 0, 1]] for c in cams])
+    intrinsics = np.stack([K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]], axis=1)
+    inv_mid = np.linalg.inv(cams[n - 1].c2w_mat)
+    c2w = np.array([inv_mid @ c.c2w_mat for c in cams], dtype=np.float32)
+    sid = n - 1 - np.arange(n)
+    tid = n - 1 + np.arange(n)
+    s2t = np.linalg.inv(c2w[tid].astype(np.float64)) @ c2w[sid]
+    Fm = torch.as_tensor(calc_fundamental_matrix(s2t, K[sid], K[tid])).float()
+    fold = np.concatenate([sid, tid])
+    return dict(F_mats=torch.cat([Fm, Fm.permute(0, 2, 1)], dim=0).contiguous(),
+                c2w=torch.from_numpy(np.ascontiguousarray(c2w[fold])).float(), K=np.ascontiguousarray(K[fold]),
+                intrinsics=torch.from_numpy(np.ascontiguousarray(intrinsics[fold])).float(), fold_indices=fold,
+                c2w_all=c2w, intrinsics_all=intrinsics)
+
+
 def pairwise_fundamental_matrices(c2w, K, video_id, n_frames=16):
     """Per-UNet-call F for a view pairing (pipeline_animation_epi_advanced.py:636-647):
     row (v, f) gets F of source (v, f) -> target (video_id[v], f).  c2w [V*n,4,4], K [V*n,3,3]."""

@@ -131,3 +131,30 @@ def training_step(pose_adaptor, optimizer, schedule, latents, noise, timesteps, 
     optimizer.step()
     optimizer.zero_grad(set_to_none=True)
     return loss.detach(), total_norm.detach()
+
+
+def fold_batch(batch, latents_like=None):
+    """The reshaping between the training dataset's batch and the step (``train_epi_control.py:518-545,577-582``): every
+    per-frame tensor of a folded clip [b, 2n, ...] becomes the two videos of a pair stacked on the batch axis [2b, n, ...]
+    (``torch.cat(x.chunk(2, dim=1), dim=0)``): ``F_mats`` / ``H_mats`` [2b, n, 3, 3]; ``plucker_embedding`` additionally to
+    channels-first [2b, 6, n, H, W]; ``warped_masks`` [b, 2n, 256, 256] min-pooled 8 x 8 down to the latent grid
+    [2b, 1, n, 32, 32] (a latent pixel counts only if every image pixel under it is valid).  Keys that are absent stay
+    absent (None).  ``latents_like``: tensor whose dtype the matrices / masks take (``type_as(latents)``)."""
+    def pair(x):
+        return torch.cat(x.chunk(2, dim=1), dim=0)
+
+    def typed(x):
+        return x if latents_like is None else x.type_as(latents_like)
+    out = {"F_mats": None, "H_mats": None, "warped_masks": None, "plucker_embedding": None}
+    if "F_mats" in batch:
+        out["F_mats"] = typed(pair(batch["F_mats"]))
+    if "H_mats" in batch:
+        out["H_mats"] = typed(pair(batch["H_mats"]))
+        m = typed(pair(batch["warped_masks"]))                               # [2b, n, 256, 256]
+        assert m.shape[-1] == 256
+        b2, n, H, W = m.shape
+        m = m.view(b2, n, H // 8, 8, W // 8, 8).permute(0, 1, 2, 4, 3, 5).reshape(b2, n, H // 8, W // 8, 64)
+        out["warped_masks"] = m.min(dim=-1)[0][:, None].float()
+    if "plucker_embedding" in batch:
+        out["plucker_embedding"] = pair(batch["plucker_embedding"]).permute(0, 2, 1, 3, 4)      # b f c h w -> b c f h w
+    return out

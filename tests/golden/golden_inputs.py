@@ -260,3 +260,26 @@ PIPE_POSE_ENCODER_KWARGS = dict(downscale_factor=8, channels=[32, 64], nums_rb=2
 PIPE_MV = dict(view_num=4, cam_pattern="interpolate", camera_dist=0.5, height=64, width=64, num_inference_steps=3,
                guidance_scale=4.0, multistep=2, accumulate_step=2)
 PIPE_SEED = 9100
+
+
+# ---- one batch of the TRAINING dataset (dataset_train_realestate10k.py: get_batch) on a synthetic 40-frame camera file -------
+TRAIN_BATCH = dict(n_cams=40, image_hw=(360, 640), sample_stride=8, random_seed=5, seed=9300)
+
+
+def write_synthetic_pose_file(path, n=40, seed=9300):
+    """A RealEstate10K-format camera file (header line, then ``id fx fy cx cy 0 0 w2c[3x4]`` per frame) of a smooth
+    trajectory: the shipped pose files hold 16 frames, the training dataset needs at least 31."""
+    rs = np.random.RandomState(seed)
+    axis = rs.standard_normal(3)
+    axis /= np.linalg.norm(axis)
+    drift = 0.03 * rs.standard_normal(3)
+    with open(path, "w") as fh:
+        fh.write("https://example.invalid/synthetic\n")
+        for i in range(n):
+            ang = 0.012 * i + 0.002 * np.sin(0.7 * i)
+            Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+            Rm = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * (Kx @ Kx)
+            tvec = drift * i + 0.01 * np.array([np.sin(0.3 * i), np.cos(0.2 * i), 0.5 * np.sin(0.1 * i)])
+            w2c = np.concatenate([Rm, tvec[:, None]], axis=1).reshape(-1)
+            vals = [1000 + 33 * i, 0.49 + 0.001 * i, 0.87, 0.5, 0.5, 0.0, 0.0] + [float(v) for v in w2c]
+            fh.write(" ".join(repr(float(v)) if k else str(int(v)) for k, v in enumerate(vals)) + "\n")

@@ -483,6 +483,32 @@ def pipeline_mv():
     save("pipeline_mv", **out)
 
 
+def train_batch():
+    """One batch of the reference's TRAINING dataset (dataset_train_realestate10k.py: RealEstate10KPoseFolded.get_batch
+    executed verbatim; image decoding stubbed to a blank 360x640 frame, the annotation index replaced by one entry) on a
+    synthetic 40-frame camera file: F matrices, folded cameras / intrinsics and Pluecker rays of the two videos."""
+    import random
+    import tempfile
+    import types
+    from animatediff.data import dataset_train_realestate10k as D
+    cfg = gi.TRAIN_BATCH
+    with tempfile.TemporaryDirectory() as tmp:
+        pose = os.path.join(tmp, "clip.txt")
+        gi.write_synthetic_pose_file(pose, cfg["n_cams"], cfg["seed"])
+        ds = object.__new__(D.RealEstate10KPoseFolded)
+        ds.root_path, ds.sample_stride, ds.sample_n_frames, ds.sample_size = tmp, cfg["sample_stride"], 16, (256, 256)
+        ds.validation_prompts = ds.validation_negative_prompts = ds.validation_video_split = None
+        ds.pose_file_0 = ds.pose_file_1 = None
+        ds.dataset = [{"clip_name": "clip", "clip_path": tmp, "caption": "a room", "pose_file": "clip.txt"}]
+        ds.pixel_transforms = lambda x: x
+        H, W = cfg["image_hw"]
+        D.imageio = types.SimpleNamespace(imread=lambda path: np.zeros((H, W, 3), dtype=np.uint8))
+        random.seed(cfg["random_seed"])
+        _pix, _cap, plucker_embedding, F_mats, _name, _vp, _vn, ret_c2w, ret_K = ds.get_batch(0, 0)
+    save("train_batch", F_mats=F_mats, c2w=ret_c2w[0], K=ret_K, plucker_sub=plucker_embedding[::3, :, ::17, ::19],
+         plucker_shape=np.array(plucker_embedding.shape))
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -504,7 +530,10 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv", "train_batch"):
+        if sys.argv[1] == "train_batch":
+            train_batch()
+            sys.exit(0)
         if sys.argv[1] == "pipeline_mv":
             pipeline_mv()
             sys.exit(0)
@@ -532,3 +561,4 @@ if __name__ == "__main__":
     train_step(Fm)
     train_step(Fm, gpu=True)
     pipeline_mv()
+    train_batch()

@@ -237,3 +237,53 @@ def test_gpu_local_cpu_binding_helpers(tmp_path, monkeypatch):
     props.pci_bus_id = 0x2c                                                              # unknown device: no sysfs entry
     assert sharding.gpu_local_cpus(0, str(tmp_path)) is None and sharding.bind_host_thread_near_gpu(0, str(tmp_path)) is None
     sharding.restore_host_affinity(None)
+
+
+def test_training_batch_conditioning_matches_reference_dataset(tmp_path):
+    """geometry.sample_clip_frames + folded_clip_conditioning against ONE batch of the reference's training dataset
+    (RealEstate10KPoseFolded.get_batch of dataset_train_realestate10k.py executed verbatim, tests/golden/train_batch.npz):
+    the same frames from the same ``random`` seed, F matrices (and their transposes for the way back), folded cameras,
+    intrinsics of the centre-cropped non-square image, and the Pluecker rays (oracle restatement of ray_condition)."""
+    import os
+    import random
+    from cvd_b200 import geometry
+    from oracle import epi_oracle as O
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_batch.npz"))
+    cfg = gi.TRAIN_BATCH
+    pose = str(tmp_path / "clip.txt")
+    gi.write_synthetic_pose_file(pose, cfg["n_cams"], cfg["seed"])
+    random.seed(cfg["random_seed"])
+    frames = geometry.sample_clip_frames(cfg["n_cams"], 16, cfg["sample_stride"])
+    assert len(frames) == 31 and frames[0] >= 0 and frames[-1] < cfg["n_cams"]
+    cond = geometry.folded_clip_conditioning(pose, frames, cfg["image_hw"])
+    Fm, Fr = cond["F_mats"].numpy(), g["F_mats"]
+    assert Fm.shape == Fr.shape == (32, 3, 3)
+    scale = np.abs(Fr).max(axis=(1, 2), keepdims=True)
+    assert np.abs(Fm - Fr).max() / scale.max() < 2e-4 and np.all(np.abs(Fm - Fr) <= 2e-4 * scale + 1e-7)
+    np.testing.assert_allclose(Fm[16:], np.transpose(Fm[:16], (0, 2, 1)))
+    np.testing.assert_allclose(cond["c2w"].numpy(), g["c2w"], atol=1e-6)
+    np.testing.assert_allclose(cond["K"], g["K"], rtol=1e-6)
+    pl = np.transpose(np.asarray(O.plucker_embedding(cond["intrinsics"], cond["c2w"], 256, 256)), (0, 3, 1, 2))   # [32,6,H,W]
+    assert tuple(pl.shape) == tuple(g["plucker_shape"])
+    np.testing.assert_allclose(pl[::3, :, ::17, ::19], g["plucker_sub"], atol=2e-5)
+
+
+def test_fold_batch_matches_the_training_script_reshapes():
+    """training.fold_batch against the statements of train_epi_control.py:518-545,577-582 written out with einops."""
+    from einops import rearrange
+    from cvd_b200 import training
+    g = torch.Generator().manual_seed(3)
+    batch = {"F_mats": torch.randn(2, 32, 3, 3, generator=g), "H_mats": torch.randn(2, 32, 3, 3, generator=g),
+             "warped_masks": (torch.rand(2, 32, 256, 256, generator=g) > 0.02).double(),
+             "plucker_embedding": torch.randn(2, 32, 6, 16, 24, generator=g)}
+    lat = torch.zeros(1, dtype=torch.float32)
+    out = training.fold_batch(batch, lat)
+    F_ref = torch.cat(batch["F_mats"].chunk(2, dim=1), dim=0).type_as(lat)
+    wm = torch.cat(batch["warped_masks"].chunk(2, dim=1), dim=0).type_as(lat)
+    wm = rearrange(wm, "b f (h h1) (w w1) -> b f h w (h1 w1)", h1=8, w1=8).min(dim=-1)[0][:, None].float()
+    pl = rearrange(torch.cat(batch["plucker_embedding"].chunk(2, dim=1), dim=0), "b f c h w -> b c f h w")
+    assert torch.equal(out["F_mats"], F_ref) and out["F_mats"].shape == (4, 16, 3, 3)
+    assert torch.equal(out["warped_masks"], wm) and wm.shape == (4, 1, 16, 32, 32) and 0 < float(wm.mean()) < 1
+    assert torch.equal(out["plucker_embedding"], pl) and pl.shape == (4, 6, 16, 16, 24)
+    only_F = training.fold_batch({"F_mats": batch["F_mats"]})
+    assert only_F["H_mats"] is None and only_F["warped_masks"] is None and only_F["plucker_embedding"] is None
