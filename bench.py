@@ -503,7 +503,7 @@ def reference_gpu_extra(dev, F_rows):
 
 
 EXTRA_KEYS = ("roofline_glue", "reference_gpu", "full_unet")
-EXTRAS_TIMEOUT_S = 600
+EXTRAS_TIMEOUT_S = 300
 LATE_TIMEOUT_S = 300         # N > 1: graph replay + config-4 measurement together (seconds of GPU work when healthy)
 
 
