@@ -1073,6 +1073,7 @@ def run_ours(args):
         return
     timer.cancel()
     emit()
+    dist.barrier()      # the other ranks start tearing NCCL down (and logging it, under NCCL_DEBUG=INFO) after the line is out
     dist.destroy_process_group()
 
 
