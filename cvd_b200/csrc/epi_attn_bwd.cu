@@ -357,6 +357,9 @@ extern "C" int cvd_epi_attn_bwd(const void* q, const void* k, const void* v, con
   CVD_REQUIRE(N == feat * feat, "cvd_epi_attn_bwd: N=%d is not feat^2 (feat=%d)", N, feat);
   CVD_REQUIRE((((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)d_out) & 15) == 0,
               "cvd_epi_attn_bwd: q/k/v/out/d_out must be 16-byte aligned");
+  // refuse before the first launch (the delta kernel below is shape-agnostic)
+  if (!((head_dim == 40 || head_dim == 80 || head_dim == 160) && N % 16 == 0))
+    return fail(CVD_E_INVALID, "cvd_epi_attn_bwd: (head_dim=%d, N=%d) is not an instantiated configuration", head_dim, N);
   cudaStream_t st = (cudaStream_t)stream;
   const long long items = (long long)R * N * heads;
   bwd::attn_bwd_delta_kernel<<<(unsigned)((items + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)d_out,

@@ -65,3 +65,47 @@ def test_kernels_are_blackwell_native(lib_path):
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS"
     assert "HGMMA" not in sass
+
+
+def test_device_shape_limits_are_refused_before_any_launch_and_match_the_test_double(lib_path, monkeypatch):
+    """What the device kernels are not instantiated for is refused by argument validation, before any CUDA call (so it can
+    be checked on a box without a GPU), and tests/emulated_ops.py in strict mode refuses the same shapes -- the CPU dry
+    run of the GPU suite (CVD_TEST_EMULATE=1) therefore fails where the device would."""
+    import torch
+    import emulated_ops
+    from cvd_b200 import _lib, ops
+    lib = _lib.load()
+    P = 1 << 20                                     # any non-null, 16-byte aligned address: never dereferenced on these paths
+    cases = [
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 24 * 24, 8, 40, 1, 24, 256.0, None), b"not an instantiated"),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 1024, 8, 48, 1, 32, 256.0, None), b"not an instantiated"),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 16, 8, 40, 3, 4, 256.0, None), b"partners"),
+        ("cvd_epi_attn_fwd", (P + 8, P, P, P, P, P, 2, 2, 1024, 8, 40, 1, 32, 256.0, None), b"16-byte aligned"),
+        ("cvd_epi_attn_fwd_lse", (P, P, P, P, P, P, P, 2, 2, 1024, 8, 48, 1, 32, 256.0, None), b"not an instantiated"),
+        ("cvd_epi_attn_bwd", (P, P, P, P, P, P, P, P, P, P, P, P, 2, 2, 1024, 8, 48, 32, 256.0, None), b"not an instantiated"),
+        ("cvd_epi_attn_bwd", (P, P, P, P, P, P, P, P, P, P, P, P, 2, 2, 100, 8, 40, 10, 256.0, None), b"not an instantiated"),
+        ("cvd_layernorm_fwd", (P, P, P, None, P, 4, 128, 1, 1e-5, None), b"not supported"),
+        ("cvd_residual_layernorm_fwd", (P, P, None, 1.0, P, P, None, P, 4, 96, 1, 1e-5, None), b"not supported"),
+        ("cvd_geglu_fwd", (P, P, 4, 13, None), b"multiple of 8"),
+        ("cvd_temporal_attn_fwd", (P, P, P, P, 4, 33, 8, 40, None), b"F=33"),
+        ("cvd_temporal_attn_fwd", (P, P, P, P, 4, 16, 8, 41, None), b"head_dim=41"),
+        ("cvd_groupnorm_tokens_fwd", (P, 0, P, P, P, P, 2, 30, 16, 64, 32, 1e-5, 0, None), b"bad shape"),
+    ]
+    for name, args, msg in cases:
+        rc = getattr(lib, name)(*args)
+        assert rc == -1 and msg in lib.cvd_last_error(), (name, rc, lib.cvd_last_error())
+    # the same shapes through the strict test double
+    emulated_ops.install(monkeypatch, strict_shapes=True)
+    bf = torch.bfloat16
+
+    def refused(fn, *a, **k):
+        with pytest.raises(_lib.CvdError):
+            fn(*a, **k)
+    part = torch.tensor([1, 0], dtype=torch.int32)
+    refused(ops.epi_attn_fwd, torch.zeros(2, 576, 320, dtype=bf), torch.zeros(2, 576, 320, dtype=bf),
+            torch.zeros(2, 8, 48, 576, dtype=bf), torch.zeros(2, 12), part, 8, 256.0)                       # (40, 24)
+    refused(ops.epi_attn_fwd, torch.zeros(2, 1024, 384, dtype=bf), torch.zeros(2, 1024, 384, dtype=bf),
+            torch.zeros(2, 8, 64, 1024, dtype=bf), torch.zeros(2, 12), part, 8, 256.0)                      # (48, 32)
+    refused(ops.layernorm, torch.zeros(4, 128), torch.ones(128), torch.zeros(128))
+    refused(ops.geglu, torch.zeros(4, 26, dtype=bf))
+    refused(ops.temporal_attn, *(torch.zeros(4, 33, 320, dtype=bf),) * 3, 8)
