@@ -109,3 +109,43 @@ def test_device_shape_limits_are_refused_before_any_launch_and_match_the_test_do
     refused(ops.layernorm, torch.zeros(4, 128), torch.ones(128), torch.zeros(128))
     refused(ops.geglu, torch.zeros(4, 26, dtype=bf))
     refused(ops.temporal_attn, *(torch.zeros(4, 33, 320, dtype=bf),) * 3, 8)
+
+
+def test_empty_and_degenerate_sizes_are_refused_not_launched(lib_path):
+    """Edge cases of every entry point -- empty batches, zero heads / partners / frames, non-square latents, unknown layout
+    and dtype codes, negative counts -- come back as CVD_E_INVALID with a message (a zero-sized grid would be a CUDA launch
+    error; PyTorch's silent empty result is not reproduced: the product fails loudly)."""
+    from cvd_b200 import _lib
+    lib = _lib.load()
+    P = 1 << 20
+    cases = [
+        ("cvd_epi_row_params", (P, P, P, 0, 32, 256.0, 2.0, 0.5, 0, 16, None)),
+        ("cvd_epi_row_params", (P, P, P, 4, 0, 256.0, 2.0, 0.5, 0, 16, None)),
+        ("cvd_epi_row_params", (P, P, P, 4, 128, 256.0, 2.0, 0.5, 0, 16, None)),
+        ("cvd_epi_bias_dense", (P, P, 0, 8, 256.0, None)),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 0, 2, 1024, 8, 40, 1, 32, 256.0, None)),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 0, 1024, 8, 40, 1, 32, 256.0, None)),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 1024, 0, 40, 1, 32, 256.0, None)),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 1024, 8, 40, 0, 32, 256.0, None)),
+        ("cvd_epi_attn_fwd", (P, P, P, P, P, P, 2, 2, 1000, 8, 40, 1, 32, 256.0, None)),
+        ("cvd_epi_attn_bwd", (P, P, P, P, P, P, P, P, P, P, P, P, 0, 2, 1024, 8, 40, 32, 256.0, None)),
+        ("cvd_layernorm_fwd", (P, P, P, None, P, 0, 320, 1, 1e-5, None)),
+        ("cvd_layernorm_fwd", (P, P, P, P, P, 4, 320, 0, 1e-5, None)),
+        ("cvd_residual_add_fwd", (P, P, None, 1.0, None, 0, 320, None)),
+        ("cvd_residual_add_fwd", (P, P, None, 1.0, None, 4, 321, None)),
+        ("cvd_geglu_fwd", (P, P, 0, 16, None)),
+        ("cvd_tokens_to_video_fwd", (P, P, P, P, 0, 0, 320, 16, 64, 0, None)),
+        ("cvd_tokens_to_video_fwd", (P, P, P, P, 0, 2, 320, 16, 64, 7, None)),
+        ("cvd_temporal_attn_fwd", (P, P, P, P, 0, 16, 8, 40, None)),
+        ("cvd_add_pose_tokens_fwd", (P, P, 0, P, 0, 320, 16, 64, None)),
+        ("cvd_scale_add_fwd", (P, P, 1.0, P, 0, None)),
+        ("cvd_scale_add_fwd", (P, P, 1.0, P, -5, None)),
+        ("cvd_pairwise_fundamental", (P, P, P, P, 0, None)),
+        ("cvd_plucker_embedding", (P, P, None, P, 0, 8, 8, 1, None)),
+        ("cvd_plucker_embedding", (P, P, None, P, 2, 0, 8, 1, None)),
+        ("cvd_groupnorm_tokens_fwd", (P, 0, P, P, P, P, 0, 320, 16, 64, 32, 1e-5, 0, None)),
+        ("cvd_groupnorm_tokens_fwd", (P, 5, P, P, P, P, 2, 320, 16, 64, 32, 1e-5, 0, None)),
+    ]
+    for name, args in cases:
+        rc = getattr(lib, name)(*args)
+        assert rc == -1 and name.encode() in lib.cvd_last_error(), (name, args, rc, lib.cvd_last_error())
