@@ -224,6 +224,51 @@ class UNet3DConditionModelPoseCond(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = InflatedConv3d(ch[0], out_channels, kernel_size=3, padding=1)
 
+    # -- checkpoints (unet.py:862-912) ------------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None, logger=None, **overrides):
+        """Build the 3-D UNet from a Stable-Diffusion 2-D UNet folder, like the reference: ``config.json`` (block types
+        replaced by their 3-D names, private ``_*`` keys dropped) + ``unet_additional_kwargs`` -> constructor; then
+        ``diffusion_pytorch_model.safetensors`` loaded non-strictly (the motion / epi modules and pose-adaptor processors
+        stay at their initial values until their own checkpoints are loaded, ``inference_epi.py:96-131``); unexpected keys
+        are an error.  ``overrides``: constructor arguments of this package only (e.g. ``amp=False``)."""
+        import json
+        import os
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        config_file = os.path.join(pretrained_model_path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file, "r") as f:
+            config = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        config["down_block_types"] = ["CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"]
+        config["up_block_types"] = ["UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"]
+        config.update(unet_additional_kwargs or {})
+        config.update(overrides)
+        model = cls(**config)
+        model_file = os.path.join(pretrained_model_path, "diffusion_pytorch_model.safetensors")
+        if not os.path.isfile(model_file):
+            raise RuntimeError(f"{model_file} does not exist")
+        import safetensors.torch
+        state_dict = safetensors.torch.load_file(model_file, device="cpu")
+        missing, unexpected = model.load_state_dict(state_dict, strict=False)
+        if logger is not None:
+            logger.info(f"Missing keys: {len(missing)}; Unexpected keys: {len(unexpected)};")
+        assert len(unexpected) == 0, unexpected[:5]
+        return model
+
+    def set_image_layer_lora_scale(self, lora_scale: float = 1.0):
+        """unet.py:338-341.  Recorded on the blocks like the reference does; it scales the image-layer LoRA processors, which
+        this package does not build (``set_all_attn_processor(add_spatial_lora=True)`` raises), so it changes nothing here
+        -- the training script calls it unconditionally (``train_epi_control.py:208,582,642``)."""
+        for block in list(self.down_blocks) + list(self.up_blocks) + [self.mid_block]:
+            block.lora_scale = lora_scale
+
+    def set_motion_module_lora_scale(self, lora_scale: float = 1.0):
+        """unet.py:343-346 (same remark: motion LoRA processors are not built)."""
+        for block in list(self.down_blocks) + list(self.up_blocks) + [self.mid_block]:
+            block.motion_lora_scale = lora_scale
+
     # -- processors (unet.py:985-1143, the branch the inference / training scripts take) ---------------------------------
     def set_all_attn_processor(self, add_spatial=False, spatial_attn_names="attn1", add_temporal=False, add_spatial_lora=False,
                                add_motion_lora=False, temporal_attn_names="0", pose_feature_dimensions=(320, 640, 1280, 1280),

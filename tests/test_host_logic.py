@@ -287,3 +287,47 @@ def test_fold_batch_matches_the_training_script_reshapes():
     assert torch.equal(out["plucker_embedding"], pl) and pl.shape == (4, 6, 16, 16, 24)
     only_F = training.fold_batch({"F_mats": batch["F_mats"]})
     assert only_F["H_mats"] is None and only_F["warped_masks"] is None and only_F["plucker_embedding"] is None
+
+
+def test_unet_from_pretrained_2d_loads_a_stable_diffusion_folder(tmp_path):
+    """UNet3DConditionModelPoseCond.from_pretrained_2d (unet.py:862-912): a Stable-Diffusion-style 2-D UNet folder
+    (config.json with the 2-D block names and diffusers' bookkeeping keys + diffusion_pytorch_model.safetensors) becomes the
+    3-D UNet with motion / epi modules; the 2-D weights land on the parameters of the same name, only motion / epi keys are
+    missing, unexpected keys and missing files are errors."""
+    import json
+    import safetensors.torch
+    from cvd_b200.unet import UNet3DConditionModelPoseCond
+    extra = dict(use_motion_module=True, motion_module_resolutions=[1, 2, 4, 8], motion_module_mid_block=False,
+                 motion_module_type="Vanilla", motion_module_kwargs=gi.UNET_MOTION_KWARGS, use_epi_module=True,
+                 epi_module_resolutions=[1, 2, 4, 8], epi_module_mid_block=False, epi_module_kwargs=gi.UNET_EPI_KWARGS)
+    folder = tmp_path / "sd" / "unet"
+    folder.mkdir(parents=True)
+    config = {"_class_name": "UNet2DConditionModel", "_diffusers_version": "0.6.0", "act_fn": "silu", "attention_head_dim": 8,
+              "block_out_channels": [32, 64, 64, 64], "center_input_sample": False, "cross_attention_dim": 48,
+              "down_block_types": ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], "downsample_padding": 1,
+              "flip_sin_to_cos": True, "freq_shift": 0, "in_channels": 4, "layers_per_block": 1, "mid_block_scale_factor": 1,
+              "norm_eps": 1e-05, "norm_num_groups": 8, "out_channels": 4, "sample_size": 8,
+              "up_block_types": ["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3}
+    (folder / "config.json").write_text(json.dumps(config))
+    with pytest.raises(RuntimeError, match="safetensors does not exist"):
+        UNet3DConditionModelPoseCond.from_pretrained_2d(str(tmp_path / "sd"), subfolder="unet", unet_additional_kwargs=extra)
+    with pytest.raises(RuntimeError, match="config.json does not exist"):
+        UNet3DConditionModelPoseCond.from_pretrained_2d(str(tmp_path / "nowhere"), unet_additional_kwargs=extra)
+    # the 2-D checkpoint: every parameter of a plain (no motion / epi) UNet of that configuration
+    plain = UNet3DConditionModelPoseCond(**{k: v for k, v in config.items() if not k.startswith("_") and "block_types" not in k})
+    sd2d = {k: torch.randn(v.shape, generator=torch.Generator().manual_seed(i)) for i, (k, v) in enumerate(plain.state_dict().items())}
+    safetensors.torch.save_file(sd2d, str(folder / "diffusion_pytorch_model.safetensors"))
+    m = UNet3DConditionModelPoseCond.from_pretrained_2d(str(tmp_path / "sd"), subfolder="unet", unet_additional_kwargs=extra,
+                                                        amp=False)
+    assert m.amp is False and len(m.down_blocks) == 4 and m.config["cross_attention_dim"] == 48
+    sd3d = m.state_dict()
+    assert all(torch.equal(sd3d[k], v) for k, v in sd2d.items())
+    rest = sorted(set(sd3d) - set(sd2d))
+    assert rest and all(("motion_modules." in k) or ("epi_modules." in k) for k in rest)
+    safetensors.torch.save_file(dict(sd2d, stray=torch.zeros(1)), str(folder / "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(AssertionError):
+        UNet3DConditionModelPoseCond.from_pretrained_2d(str(tmp_path / "sd"), subfolder="unet", unet_additional_kwargs=extra)
+    # the training script's unconditional LoRA-scale calls (train_epi_control.py:208,582,642)
+    m.set_image_layer_lora_scale(0.0)
+    m.set_motion_module_lora_scale(0.5)
+    assert all(b.lora_scale == 0.0 and b.motion_lora_scale == 0.5 for b in list(m.down_blocks) + list(m.up_blocks) + [m.mid_block])
