@@ -509,6 +509,25 @@ def train_batch():
          plucker_shape=np.array(plucker_embedding.shape))
 
 
+def state_keys():
+    """Full state_dict key tables (parameters AND persistent buffers, with shapes) of the reference's UNet and pose encoder:
+    the strict-load contract (inference_epi.py:118-119 loads the pose encoder with strict=True)."""
+    from animatediff.models.pose_adaptor import CameraPoseEncoder
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    out = {}
+    sd = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS).state_dict()
+    out["unet_keys"] = np.array(sorted(sd))
+    out["unet_shapes"] = np.array([str(tuple(sd[k].shape)) for k in sorted(sd)])
+    for case in gi.POSE_ENCODER_CASES:
+        sd = CameraPoseEncoder(**case["kwargs"]).state_dict()
+        out[case["name"] + "_keys"] = np.array(sorted(sd))
+        out[case["name"] + "_shapes"] = np.array([str(tuple(sd[k].shape)) for k in sorted(sd)])
+        pe = [k for k in sorted(sd) if k.endswith(".pe")]
+        if pe:
+            out[case["name"] + "_pe0"] = sd[pe[0]]
+    save("state_keys", **out)
+
+
 def plucker():
     """ray_condition of the reference (data/dataset_validation.py:102-144) on the shipped pose pair's cameras at the
     256 x 256 sample size and at a small non-square 5 x 7 grid, plus one horizontally flipped camera."""
@@ -530,7 +549,10 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv", "train_batch"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv", "train_batch", "state_keys"):
+        if sys.argv[1] == "state_keys":
+            state_keys()
+            sys.exit(0)
         if sys.argv[1] == "train_batch":
             train_batch()
             sys.exit(0)
@@ -562,3 +584,4 @@ if __name__ == "__main__":
     train_step(Fm, gpu=True)
     pipeline_mv()
     train_batch()
+    state_keys()

@@ -331,3 +331,24 @@ def test_unet_from_pretrained_2d_loads_a_stable_diffusion_folder(tmp_path):
     m.set_image_layer_lora_scale(0.0)
     m.set_motion_module_lora_scale(0.5)
     assert all(b.lora_scale == 0.0 and b.motion_lora_scale == 0.5 for b in list(m.down_blocks) + list(m.up_blocks) + [m.mid_block])
+
+
+def test_strict_state_dict_contract_including_buffers():
+    """Parameters AND persistent buffers (positional tables) of the product UNet and pose encoder carry the reference's names
+    and shapes (tests/golden/state_keys.npz), so ``load_state_dict(..., strict=True)`` of a reference checkpoint works
+    (inference_epi.py:118-119); the sinusoidal table itself equals the reference's."""
+    import os
+    import cvd_b200
+    from cvd_b200.unet import UNet3DConditionModelPoseCond
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "state_keys.npz"))
+    sd = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS).state_dict()
+    assert sorted(sd) == g["unet_keys"].tolist()
+    assert [str(tuple(sd[k].shape)) for k in sorted(sd)] == g["unet_shapes"].tolist()
+    for case in gi.POSE_ENCODER_CASES:
+        n = case["name"]
+        sd = cvd_b200.CameraPoseEncoder(**case["kwargs"]).state_dict()
+        assert sorted(sd) == g[n + "_keys"].tolist()
+        assert [str(tuple(sd[k].shape)) for k in sorted(sd)] == g[n + "_shapes"].tolist()
+        pe = [k for k in sorted(sd) if k.endswith(".pe")]
+        if pe:
+            np.testing.assert_allclose(sd[pe[0]].numpy(), g[n + "_pe0"], atol=1e-6)
