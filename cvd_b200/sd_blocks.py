@@ -98,13 +98,28 @@ class SpatialAttention(nn.Module):
         self.to_k = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
         self.to_v = nn.Linear(cross_attention_dim or query_dim, inner, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+        # attention_processor.py:21-23,67-79 (AttnProcessor(attn_type="spatial", spatial_extended_attention=True)): every
+        # frame also attends to the same frame of the other video(s) of its pair / group -- keys and values of the batch
+        # chunks are concatenated along the token axis.  Set by UNet3DConditionModelPoseCond.set_all_attn_processor.
+        self.spatial_extended_attention = False
+
+    @staticmethod
+    def _extend(t):
+        """attention_processor.py:70-79, quirks kept: batches of more than 32 frames (= more than one pair of 16-frame
+        videos) are cut into 32-frame chunks, otherwise into two halves; the chunks are laid side by side along the token
+        axis and the result is repeated for every chunk."""
+        n = t.shape[0] // 32 if t.shape[0] > 32 else 2
+        return torch.cat(t.chunk(n), dim=1).repeat(n, 1, 1)
 
     def forward(self, x, context=None):
         B, N, _ = x.shape
         ctx = x if context is None else context
         q = self.to_q(x).view(B, N, self.heads, -1).transpose(1, 2)
-        k = self.to_k(ctx).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
-        v = self.to_v(ctx).view(B, ctx.shape[1], self.heads, -1).transpose(1, 2)
+        k, v = self.to_k(ctx), self.to_v(ctx)
+        if self.spatial_extended_attention and k.shape[1] != 77:      # ":68": anything but a 77-token text context
+            k, v = self._extend(k), self._extend(v)
+        k = k.view(B, k.shape[1], self.heads, -1).transpose(1, 2)
+        v = v.view(B, v.shape[1], self.heads, -1).transpose(1, 2)
         o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, -1)
         return self.to_out[0](o)
 

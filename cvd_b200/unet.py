@@ -274,8 +274,11 @@ class UNet3DConditionModelPoseCond(nn.Module):
                                add_motion_lora=False, temporal_attn_names="0", pose_feature_dimensions=(320, 640, 1280, 1280),
                                lora_kwargs=None, motion_lora_kwargs=None, sync_lora_kwargs=None,
                                spatial_extended_attention=False, **attention_processor_kwargs):
-        if add_spatial or add_spatial_lora or add_motion_lora or spatial_extended_attention:
-            raise NotImplementedError("spatial pose adaptors, LoRA processors and extended spatial attention are not built")
+        if add_spatial or add_spatial_lora or add_motion_lora:
+            raise NotImplementedError("spatial pose adaptors and LoRA processors are not built")
+        for module in self.modules():                       # unet.py:1062: AttnProcessor(attn_type="spatial", ...)
+            if isinstance(module, sd.SpatialAttention):
+                module.spatial_extended_attention = bool(spatial_extended_attention)
         if sync_lora_kwargs and (sync_lora_kwargs.get("sync_lora_rank", 0) or sync_lora_kwargs.get("sync_lora_scale", 0)):
             raise NotImplementedError("sync LoRA is unused at inference (inference_epi.py:84) and not built")
         names = set(temporal_attn_names.split(","))

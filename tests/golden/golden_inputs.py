@@ -283,3 +283,9 @@ def write_synthetic_pose_file(path, n=40, seed=9300):
             w2c = np.concatenate([Rm, tvec[:, None]], axis=1).reshape(-1)
             vals = [1000 + 33 * i, 0.49 + 0.001 * i, 0.87, 0.5, 0.5, 0.0, 0.0] + [float(v) for v in w2c]
             fh.write(" ".join(repr(float(v)) if k else str(int(v)) for k, v in enumerate(vals)) + "\n")
+
+
+def text77(seed=UNET_SEED + 7, text_dim=48):
+    """A CLIP-length (77-token) text context for the UNet fixture (the reference tells text from image tokens by that length)."""
+    rs = np.random.RandomState(seed)
+    return torch.from_numpy((0.5 * rs.standard_normal((2, 77, text_dim))).astype(np.float32))

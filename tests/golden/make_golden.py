@@ -509,6 +509,32 @@ def train_batch():
          plucker_shape=np.array(plucker_embedding.shape))
 
 
+def unet_extended(Fm):
+    """The reference UNet with ``spatial_extended_attention=True`` (AttnProcessor of attention_processor.py:67-79 on the SD
+    spatial attention): one forward with the 7-token text of the UNet fixture (the quirk: any context that is not 77 tokens
+    long is extended too), one with a 77-token text (cross-attention untouched), one on a 4-video batch (> 32 frames: the
+    32-frame chunking)."""
+    from animatediff.models.unet import UNet3DConditionModelPoseCond
+    m = UNet3DConditionModelPoseCond(**gi.UNET_KWARGS)
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=True,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    m.eval()
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    m.load_state_dict(gi.fill_state_dict(shapes, gi.UNET_SEED), strict=False)
+    lat, text, poses = gi.unet_inputs()
+    F2 = Fm.reshape(2, 16, 3, 3)
+    out = {"t7": m(lat, 481, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample}
+    text77 = gi.text77()
+    out["t77"] = m(lat, 481, encoder_hidden_states=text77, F_mats=F2, pose_embedding_features=poses).sample
+    lat4 = torch.cat([lat, lat.flip(0) * 0.5])
+    out["b4"] = m(lat4, 481, encoder_hidden_states=torch.cat([text77, text77 * 0.5]), F_mats=torch.cat([F2, F2]),
+                  pose_embedding_features=[torch.cat([p, p.flip(0)]) for p in poses]).sample
+    save("unet_ext", **out)
+
+
 def state_keys():
     """Full state_dict key tables (parameters AND persistent buffers, with shapes) of the reference's UNet and pose encoder:
     the strict-load contract (inference_epi.py:118-119 loads the pose encoder with strict=True)."""
@@ -549,7 +575,10 @@ def plucker():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv", "train_batch", "state_keys"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("plucker", "bias_pseudo", "pose_encoder", "unet", "train_step", "pipeline_mv", "train_batch", "state_keys", "unet_ext"):
+        if sys.argv[1] == "unet_ext":
+            unet_extended(torch.from_numpy(np.load(os.path.join(HERE, "geometry.npz"))["F_mats"]))
+            sys.exit(0)
         if sys.argv[1] == "state_keys":
             state_keys()
             sys.exit(0)
@@ -585,3 +614,4 @@ if __name__ == "__main__":
     pipeline_mv()
     train_batch()
     state_keys()
+    unet_extended(Fm)

@@ -572,3 +572,42 @@ def test_multiview_pipeline_from_camera_rig_to_latents(monkeypatch):
     err = rel_l2(out, t(g["final"]))
     assert out.shape == lat4.shape and err < 5e-2, err
     print(f"multiview pipeline final latents rel_l2 {err:.2e}")
+
+
+def test_unet_spatial_extended_attention_vs_reference(golden, monkeypatch):
+    """``set_all_attn_processor(spatial_extended_attention=True)``: the SD self-attention of every frame also reads the same
+    frame of the partner video (attention_processor.py:67-79).  Against the reference UNet (tests/golden/unet_ext.npz): the
+    7-token text of the fixture (extended too -- only 77-token contexts are exempt), a 77-token text, and a 4-video batch
+    (the 32-frame chunking); switching it off again restores the plain UNet."""
+    emulated_ops.install(monkeypatch)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_ext.npz"))
+    m = _product_unet()
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=True,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    skip = ("pos_encoder.pe", "pos_encoder.coords")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.endswith(skip)}
+    m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    lat, text, poses = gi.unet_inputs()
+    text77 = gi.text77()
+    F2 = t(golden["geometry"]["F_mats"]).reshape(2, 16, 3, 3)
+    with torch.no_grad():
+        o7 = m(lat, 481, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample
+        o77 = m(lat, 481, encoder_hidden_states=text77, F_mats=F2, pose_embedding_features=poses).sample
+        lat4 = torch.cat([lat, lat.flip(0) * 0.5])
+        o4 = m(lat4, 481, encoder_hidden_states=torch.cat([text77, text77 * 0.5]), F_mats=torch.cat([F2, F2]),
+               pose_embedding_features=[torch.cat([p, p.flip(0)]) for p in poses]).sample
+    errs = {name: rel_l2(o, t(g[name])) for name, o in (("t7", o7), ("t77", o77), ("b4", o4))}
+    print("spatial extended attention rel_l2:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 1e-2, errs
+    plain = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet.npz"))
+    assert rel_l2(o7, t(plain["sample_t481"])) > 3 * max(errs.values())    # the option matters: far outside the parity error
+    m.set_all_attn_processor(add_spatial_lora=False, add_motion_lora=False, lora_kwargs={"lora_rank": 2, "lora_scale": 1.0},
+                             motion_lora_kwargs={"lora_rank": -1, "lora_scale": 1.0},
+                             sync_lora_kwargs={"sync_lora_rank": 0, "sync_lora_scale": 0}, spatial_extended_attention=False,
+                             **gi.UNET_PROCESSOR_KWARGS)
+    m.load_state_dict(gi.fill_state_dict(mine, gi.UNET_SEED), strict=False)
+    with torch.no_grad():
+        assert rel_l2(m(lat, 481, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample,
+                      t(plain["sample_t481"])) < REL
