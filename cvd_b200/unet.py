@@ -155,6 +155,16 @@ class _Block3D(nn.Module):
         return (x, outputs, aux) if self.kind == "down" else (x, aux)
 
 
+class _Config(dict):
+    """Constructor arguments with attribute access, like diffusers' FrozenDict (``unet.config.sample_size``)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
 class UNet3DConditionModelPoseCond(nn.Module):
     """``unet.py:56-330`` (constructor), ``:1145-1452`` (forward), for the block layout every shipped config uses."""
 
@@ -178,8 +188,12 @@ class UNet3DConditionModelPoseCond(nn.Module):
             raise NotImplementedError("only the SD-1.5 block configuration is built")
         motion_module_kwargs = dict(motion_module_kwargs or {})
         epi_module_kwargs = dict(epi_module_kwargs or {})
-        self.config = dict(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
-                           cross_attention_dim=cross_attention_dim, sample_size=sample_size, layers_per_block=layers_per_block)
+        # what the reference's scripts and pipelines read off the UNet (diffusers ModelMixin / ConfigMixin surface):
+        # unet.config.sample_size / ["in_channels"] / dict(unet.config), unet.in_channels, unet.device, unet.dtype
+        self.config = _Config(in_channels=in_channels, out_channels=out_channels, block_out_channels=tuple(block_out_channels),
+                              cross_attention_dim=cross_attention_dim, sample_size=sample_size, layers_per_block=layers_per_block,
+                              attention_head_dim=attention_head_dim, norm_num_groups=norm_num_groups)
+        self.in_channels = in_channels
         self.decoder_add_posecond = decoder_add_posecond
         self.amp = amp                     # bf16 autocast for the SD blocks (False: fp32, parity tests against the reference)
         self.flip_sin_to_cos, self.freq_shift = flip_sin_to_cos, freq_shift
@@ -223,6 +237,14 @@ class UNet3DConditionModelPoseCond(nn.Module):
         self.conv_norm_out = nn.GroupNorm(num_channels=ch[0], num_groups=norm_num_groups, eps=norm_eps)
         self.conv_act = nn.SiLU()
         self.conv_out = InflatedConv3d(ch[0], out_channels, kernel_size=3, padding=1)
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
 
     # -- checkpoints (unet.py:862-912) ------------------------------------------------------------------------------------
     @classmethod

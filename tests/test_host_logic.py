@@ -320,6 +320,9 @@ def test_unet_from_pretrained_2d_loads_a_stable_diffusion_folder(tmp_path):
     m = UNet3DConditionModelPoseCond.from_pretrained_2d(str(tmp_path / "sd"), subfolder="unet", unet_additional_kwargs=extra,
                                                         amp=False)
     assert m.amp is False and len(m.down_blocks) == 4 and m.config["cross_attention_dim"] == 48
+    # the surface the reference's scripts / pipelines read (pipeline_animation_epi.py:91-110,512,549; inference_epi.py:93)
+    assert m.config.sample_size == 8 and m.in_channels == 4 and m.device == torch.device("cpu") and m.dtype == torch.float32
+    assert not hasattr(m.config, "_diffusers_version") and dict(m.config)["in_channels"] == 4
     sd3d = m.state_dict()
     assert all(torch.equal(sd3d[k], v) for k, v in sd2d.items())
     rest = sorted(set(sd3d) - set(sd2d))
