@@ -611,3 +611,73 @@ def test_unet_spatial_extended_attention_vs_reference(golden, monkeypatch):
     with torch.no_grad():
         assert rel_l2(m(lat, 481, encoder_hidden_states=text, F_mats=F2, pose_embedding_features=poses).sample,
                       t(plain["sample_t481"])) < REL
+
+
+# ---- MultiviewPipeline, view-sharded over two gloo ranks ------------------------------------------------------------
+def _mv_pipeline_case():
+    import cvd_b200
+    enc = cvd_b200.CameraPoseEncoder(downscale_factor=8, channels=[320], nums_rb=2, cin=384, ksize=1, sk=True, use_conv=False,
+                                     temporal_attention_nhead=8, attention_block_types=["Temporal_Self"],
+                                     temporal_position_encoding=True, temporal_position_encoding_max_len=16).eval()
+    shapes = {k: tuple(v.shape) for k, v in enc.state_dict().items() if not k.endswith("pos_encoder.pe")}
+    enc.load_state_dict(gi.fill_state_dict(shapes, 9500), strict=False)
+    g = torch.Generator().manual_seed(19)
+    lat = torch.randn(4, 4, 16, 4, 4, generator=g)
+    text = torch.randn(2, 77, 768, generator=g) * 0.3
+    return enc, lat, text
+
+
+def _run_mv_pipeline(net, shard):
+    import cvd_b200
+    from cvd_b200 import ops
+    ops.pairwise_fundamental = lambda c, k, partner: _host_F(c, k, partner.numpy().astype(np.int64))
+    enc, lat, text = _mv_pipeline_case()
+    world, rank = (1, 0) if shard is None else (shard.world, shard.rank)
+    n = 4 // world
+    np.random.seed(123)
+    pipe = cvd_b200.MultiviewPipeline(net, enc)
+    return pipe(text, view_num=4, cam_pattern="upper_hemi", height=32, width=32, num_inference_steps=2, guidance_scale=4.0,
+                latents=lat[rank * n:(rank + 1) * n].clone(), shard=shard)
+
+
+def _mv_pipeline_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cvd_b200 import sampler
+        from cvd_b200.sharding import ViewShard
+        emulated_ops.install(_Patcher())
+        torch.Tensor.is_cuda = property(lambda self: True)
+        shard = ViewShard()
+        net = _unit_net()
+        sampler.install_sharding(net, shard, None)
+        ret[rank] = _run_mv_pipeline(net, shard).numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multiview_pipeline_view_sharded_world2(monkeypatch):
+    """cvd_b200.MultiviewPipeline with ``shard=ViewShard()`` on two gloo ranks (2 of the 4 views each; rig, rays and pose
+    encoder replicated, pose features / latents sliced per rank, partner rows through the layers' exchange): every rank
+    ends with its own views of the single-process result."""
+    import socket
+    import torch.multiprocessing as mp
+    from cvd_b200 import ops
+    emulated_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(ops, "pairwise_fundamental", ops.pairwise_fundamental)      # restored after _run_mv_pipeline's patch
+    ref = _run_mv_pipeline(_unit_net(), None)
+    assert ref.shape == (4, 4, 16, 4, 4) and torch.isfinite(ref).all()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_mv_pipeline_worker, args=(2, port, ret), nprocs=2, join=True)
+    for r in range(2):
+        got = torch.from_numpy(ret[r])
+        assert got.shape == (2, 4, 16, 4, 4)
+        assert rel_l2(got, ref[2 * r:2 * r + 2]) < 2e-2, (r, rel_l2(got, ref[2 * r:2 * r + 2]))
+    assert rel_l2(torch.from_numpy(ret[0]), ref[2:4]) > 5e-2                         # (the slices are not interchangeable)
