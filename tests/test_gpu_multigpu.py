@@ -20,15 +20,23 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torchrun(worker, nproc, ok_line, timeout=900):
+def _torchrun(worker, nproc, ok_line, timeout=300):
     if not torch.cuda.is_available() or torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs, this box has {torch.cuda.device_count() if torch.cuda.is_available() else 0}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multigpu", worker)]
-    res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
-    tail = res.stdout[-3000:] + "\n---- stderr ----\n" + res.stderr[-3000:]
-    assert res.returncode == 0 and ok_line in res.stdout, tail
-    return res.stdout
+    # own session: on a timeout the launcher AND its workers are ended (the process group started here, nothing else)
+    proc = subprocess.Popen(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail(f"{worker} did not finish within {timeout} s\n" + out[-2000:] + "\n---- stderr ----\n" + err[-2000:])
+    tail = out[-3000:] + "\n---- stderr ----\n" + err[-3000:]
+    assert proc.returncode == 0 and ok_line in out, tail
+    return out
 
 
 def test_layer_peer_exchange_equals_unsharded():
@@ -38,8 +46,9 @@ def test_layer_peer_exchange_equals_unsharded():
 
 
 def test_attention_reads_peer_kv_in_kernel():
-    """The attention kernels reading the partner's K / V^T straight out of the peer's HBM (TMA over NVLink, incl. the
-    cluster-multicast path for latents > 8x8) are bit-identical to the same call on a local copy."""
+    """The attention kernels reading the partner's K / V^T straight out of the peer's HBM (unicast TMA over NVLink at 8x8,
+    plain loads at 4x4; never the cluster-multicast kernels) are bit-identical to the same call on
+    a local copy."""
     _torchrun("mg_peer_direct.py", 2, "DIRECT PEER READ OK")
 
 
