@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _torchrun(worker, nproc, ok_line, timeout=300):
+def _torchrun(worker, nproc, ok_line, timeout=480):
     if not torch.cuda.is_available() or torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs, this box has {torch.cuda.device_count() if torch.cuda.is_available() else 0}")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
