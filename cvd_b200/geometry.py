@@ -157,6 +157,38 @@ def folded_clip_conditioning(pose_file, frame_indices, image_hw, sample_n_frames
                 c2w_all=c2w, intrinsics_all=intrinsics)
 
 
+def interpolate_view_poses(src_poses, tgt_poses, split_num):
+    """``RealEstate10KPoseFolded.interpolate_poses`` (dataset_train_realestate10k.py:365-384): ``split_num`` trajectories
+    between two n-frame trajectories [n,4,4] -- translation blended linearly, rotation by spherical interpolation, per
+    frame -- stacked view-major [split_num * n, 4, 4] (view 0 = ``src_poses``, view split_num - 1 = ``tgt_poses``)."""
+    from scipy.spatial.transform import Rotation, Slerp
+    src = np.asarray(src_poses)
+    tgt = np.asarray(tgt_poses)
+    n = len(src)
+    out = np.tile(src, (split_num, 1, 1))
+    w = np.linspace(0.0, 1.0, split_num)
+    for i in range(split_num):
+        alpha = i / (split_num - 1)
+        out[i * n:(i + 1) * n, :3, 3] = src[:, :3, 3] * (1 - alpha) + tgt[:, :3, 3] * alpha
+    for f in range(n):
+        ends = Rotation.from_matrix(np.stack([src[f, :3, :3], tgt[f, :3, :3]]))
+        out[f::n, :3, :3] = Slerp([0, 1], ends)(w).as_matrix()
+    return out
+
+
+def multiview_clip_conditioning(cond, split_num):
+    """The ``validation_video_split != 2`` branch of the training dataset (dataset_train_realestate10k.py:466-478): from the
+    folded two-video conditioning of :func:`folded_clip_conditioning`, ``split_num`` views interpolated between video 0
+    and video 1 -- cameras ``c2w`` float32 [split_num n, 4, 4] (what the V-view pipeline receives as ``aux_c2w``), ``K``
+    [split_num n, 3, 3] and ``intrinsics`` [split_num n, 4] (video 0's, repeated per view), the inputs of the Pluecker rays."""
+    n = cond["c2w"].shape[0] // 2
+    c2w = cond["c2w"].numpy()
+    inter = interpolate_view_poses(c2w[:n], c2w[n:], split_num)
+    intr = cond["intrinsics"][:n].repeat(split_num, 1)
+    return dict(c2w=torch.from_numpy(np.ascontiguousarray(inter)).float(), K=np.tile(cond["K"][:n], (split_num, 1, 1)),
+                intrinsics=intr.contiguous())
+
+
 def pairwise_fundamental_matrices(c2w, K, video_id, n_frames=16):
     """Per-UNet-call F for a view pairing (pipeline_animation_epi_advanced.py:636-647):
     row (v, f) gets F of source (v, f) -> target (video_id[v], f).  c2w [V*n,4,4], K [V*n,3,3]."""

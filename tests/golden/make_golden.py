@@ -505,8 +505,13 @@ def train_batch():
         D.imageio = types.SimpleNamespace(imread=lambda path: np.zeros((H, W, 3), dtype=np.uint8))
         random.seed(cfg["random_seed"])
         _pix, _cap, plucker_embedding, F_mats, _name, _vp, _vn, ret_c2w, ret_K = ds.get_batch(0, 0)
+        # the same clip as 4 interpolated views (validation_video_split = 4, :466-478)
+        ds.validation_video_split = 4
+        random.seed(cfg["random_seed"])
+        _pix, _cap, plucker4, _F4, _name, _vp, _vn, c2w4, K4 = ds.get_batch(0, 0)
     save("train_batch", F_mats=F_mats, c2w=ret_c2w[0], K=ret_K, plucker_sub=plucker_embedding[::3, :, ::17, ::19],
-         plucker_shape=np.array(plucker_embedding.shape))
+         plucker_shape=np.array(plucker_embedding.shape), mv_c2w=c2w4, mv_K=K4, mv_plucker_sub=plucker4[::5, :, ::17, ::19],
+         mv_plucker_shape=np.array(plucker4.shape))
 
 
 def unet_extended(Fm):

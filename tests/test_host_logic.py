@@ -266,6 +266,15 @@ def test_training_batch_conditioning_matches_reference_dataset(tmp_path):
     pl = np.transpose(np.asarray(O.plucker_embedding(cond["intrinsics"], cond["c2w"], 256, 256)), (0, 3, 1, 2))   # [32,6,H,W]
     assert tuple(pl.shape) == tuple(g["plucker_shape"])
     np.testing.assert_allclose(pl[::3, :, ::17, ::19], g["plucker_sub"], atol=2e-5)
+    # the same clip as 4 interpolated views (validation_video_split = 4, :466-478)
+    mv = geometry.multiview_clip_conditioning(cond, 4)
+    np.testing.assert_allclose(mv["c2w"].numpy(), g["mv_c2w"], atol=2e-6)
+    np.testing.assert_allclose(mv["K"], g["mv_K"], rtol=1e-6)
+    np.testing.assert_allclose(mv["c2w"][:16].numpy(), cond["c2w"][:16].numpy(), atol=2e-6)        # view 0 = video 0
+    np.testing.assert_allclose(mv["c2w"][48:].numpy(), cond["c2w"][16:].numpy(), atol=2e-6)        # view 3 = video 1
+    pl4 = np.transpose(np.asarray(O.plucker_embedding(mv["intrinsics"], mv["c2w"], 256, 256)), (0, 3, 1, 2))
+    assert tuple(pl4.shape) == tuple(g["mv_plucker_shape"])
+    np.testing.assert_allclose(pl4[::5, :, ::17, ::19], g["mv_plucker_sub"], atol=3e-5)
 
 
 def test_fold_batch_matches_the_training_script_reshapes():
