@@ -46,7 +46,10 @@ class PairPipeline:
             shape = (2, self.unet.config["in_channels"], video_length, height // 8, width // 8)
             latents = torch.randn(shape, generator=generator, device=dev)
         sch = self.schedule if self.schedule is not None else sampler.DDIMSchedule(device=dev)
-        return sampler.sample_pair(self.unet, latents * sch.init_noise_sigma, F_mats, text_embeddings.to(dev), sch,
+        text = text_embeddings.to(dev)
+        if guidance_scale <= 1.0:            # no guidance: the prompt embedding alone (_encode_prompt without the negative half)
+            text = text[1:]
+        return sampler.sample_pair(self.unet, latents * sch.init_noise_sigma, F_mats, text, sch,
                                    num_inference_steps, guidance_scale, pose_embedding_features=poses)
 
 

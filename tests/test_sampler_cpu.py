@@ -318,3 +318,56 @@ def test_unit_loop_sharded_equals_single_process(V, acc, world):
     for r in range(world):
         got = torch.from_numpy(ret[r])
         assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), (r, float((got - ref).abs().max()))
+
+
+def test_sample_pair_without_guidance_is_the_plain_ddim_loop():
+    """guidance_scale <= 1 (pipeline_animation_epi.py:565,604-610 with do_classifier_free_guidance False): no CFG batch, the
+    prompt embedding repeated per video, F matrices and pose features as given -- one UNet call per step on the 2 latents."""
+    calls = []
+
+    def unet(x, t, F_mats=None, encoder_hidden_states=None, pose_embedding_features=None):
+        calls.append((tuple(x.shape), tuple(F_mats.shape), tuple(encoder_hidden_states.shape),
+                      tuple(pose_embedding_features[0].shape)))
+        return 0.1 * x + 0.01 * encoder_hidden_states.mean() + 0.001 * F_mats.mean() + pose_embedding_features[0].mean()
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(2, 4, 16, 4, 4, generator=g)
+    Fm = torch.randn(2, 16, 3, 3, generator=g)
+    text = torch.randn(1, 7, 8, generator=g)
+    poses = [torch.randn(2, 6, 16, 4, 4, generator=g)]
+    sch = sampler.DDIMSchedule()
+    out = sampler.sample_pair(unet, lat.clone(), Fm, text, sch, 3, 1.0, pose_embedding_features=poses)
+    assert calls == [((2, 4, 16, 4, 4), (2, 16, 3, 3), (2, 7, 8), (2, 6, 16, 4, 4))] * 3
+    ref = lat.clone()
+    sch2 = sampler.DDIMSchedule()
+    for t in sch2.set_timesteps(3):
+        ref = sch2.step(unet(ref, t, F_mats=Fm, encoder_hidden_states=text.repeat(2, 1, 1), pose_embedding_features=poses), t, ref)
+    assert torch.equal(out, ref)
+
+
+def test_sample_multiview_without_guidance(monkeypatch):
+    """guidance_scale <= 1 in the V-view loop (pipeline_animation_epi_advanced.py:651-657, else-branches): V rows of latents,
+    text and pose features as given (not doubled), kv_index = the pairing itself (V * 16 rows), F of every (view, frame)."""
+    from cvd_b200 import geometry, ops
+    monkeypatch.setattr(ops, "pairwise_fundamental", lambda c, k, partner: geometry.pairwise_fundamental_matrices(
+        c.numpy(), k.numpy(), partner.numpy().astype(np.int64)[::16] // 16))
+    seen = []
+
+    def unet(x, t, F_mats=None, encoder_hidden_states=None, pose_embedding_features=None):
+        Fm, kv = F_mats
+        seen.append((tuple(x.shape), tuple(Fm.shape), np.asarray(kv).copy(), tuple(encoder_hidden_states.shape),
+                     tuple(pose_embedding_features[0].shape)))
+        return 0.1 * x
+    V = 4
+    g = torch.Generator().manual_seed(6)
+    lat = torch.randn(V, 4, 16, 4, 4, generator=g)
+    text = torch.randn(V, 7, 8, generator=g)
+    poses = [torch.randn(V, 6, 16, 4, 4, generator=g)]
+    c2w, K = sampler.multiview_cameras(V, 16, "circle", 0.5, 256)
+    np.random.seed(3)
+    out = sampler.sample_multiview(unet, lat.clone(), text, sampler.DDIMSchedule(), 2, 1.0, aux_c2w=c2w, aux_K_mats=K,
+                                   pose_embedding_features=poses)
+    assert out.shape == lat.shape and len(seen) == 2
+    for xs, fs, kv, ts, ps in seen:
+        assert xs == (V, 4, 16, 4, 4) and fs == (V, 16, 3, 3) and ts == (V, 7, 8) and ps == (V, 6, 16, 4, 4)
+        assert kv.shape == (V * 16,) and sorted(kv.tolist()) == list(range(V * 16))          # a permutation of the rows
+        assert np.array_equal(kv[kv], np.arange(V * 16)) and not np.any(kv == np.arange(V * 16))   # disjoint pairs
